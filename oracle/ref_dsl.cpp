@@ -1,0 +1,710 @@
+// oracle/ref_dsl.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Thin C-ABI driver around the UNMODIFIED reference DSL headers
+// (/root/reference/dsl/*.hpp, compiled where they lie) and the reference's own
+// sample kernel classes (/root/reference/samples-public/*/src/main.cpp,
+// #included where they lie with `main` renamed).  Executing a DSL program as
+// plain C++ is the reference's executable specification (dsl/kernel.hpp:94-119),
+// so this library is the "spec of record" the restated oracle (emit_cpu.cpp)
+// and the CUDA path are pinned against.
+//
+// Built by oracle/Makefile into oracle/_ref/libhipacc_ref.so (git-ignored).
+// Nothing from the reference is copied into this repository: the sample files
+// are textually included from /root/reference at build time.
+//
+// Kernels that BASELINE.json asks for in float (C2, C3, C5) do not exist as
+// samples (the samples are uchar/int); for those this file holds small DSL
+// *user programs* written against the reference DSL.
+
+#include <cstring>
+#include <cstdint>
+#include <vector>
+#include <functional>
+
+#include "hipacc.hpp"          // /root/reference/dsl
+#include <hipacc_helper.hpp>   // /root/reference/samples-public/common
+
+// ---- the reference's own sample programs, included where they lie ---------
+// Each sample defines main(), #defines and file-scope helpers; wrap each in a
+// namespace so that equally named kernel classes (Sobel, Gaussian) do not clash.
+#define main sample_main
+namespace smp_gauss {
+#include "1_Local_Operators/Gaussian_Blur/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_laplace {
+#include "1_Local_Operators/Laplace/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef SIZE
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_sobel {
+#include "3_Preprocessing/Sobel/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+#undef data_t
+namespace smp_bilateral {
+#include "3_Preprocessing/Bilateral_Filter/src/main.cpp"
+}
+#undef SIGMA_S
+#undef SIGMA_R
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_harris {
+#include "3_Preprocessing/Harris_Corner/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+#undef data_t
+namespace smp_pyr {
+#include "5_Other/Gaussian_Laplacian_Pyramid/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_redsum {
+#include "2_Global_Operators/Reduction_Sum/src/main.cpp"
+}
+#undef WIDTH
+#undef HEIGHT
+namespace smp_dilate {
+#include "1_Local_Operators/Dilate/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_box {
+#include "1_Local_Operators/Box_Blur/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+#undef main
+
+// reference CPU runtime's reduction macro (runtime/hipacc_cpu_red.hpp:19-68)
+#define USE_OPENMP
+#include "hipacc_cpu_red.hpp"
+
+using namespace hipacc;
+using namespace hipacc::math;
+
+namespace {
+
+// roi = {is_w, is_h, is_ox, is_oy, acc_w, acc_h, acc_ox, acc_oy}; NULL/<=0 => full
+struct Roi { int is_w, is_h, is_ox, is_oy, acc_w, acc_h, acc_ox, acc_oy; };
+Roi make_roi(const int *r, int w, int h) {
+    Roi o{w, h, 0, 0, w, h, 0, 0};
+    if (r) {
+        if (r[0] > 0) { o.is_w = r[0]; o.is_h = r[1]; o.is_ox = r[2]; o.is_oy = r[3]; }
+        if (r[4] > 0) { o.acc_w = r[4]; o.acc_h = r[5]; o.acc_ox = r[6]; o.acc_oy = r[7]; }
+    }
+    return o;
+}
+
+template <typename T>
+BoundaryCondition<T> make_bc(Image<T> &img, MaskBase &m, int bmode) {
+    Boundary b = static_cast<Boundary>(bmode);
+    if (b == Boundary::CONSTANT) return BoundaryCondition<T>(img, m, b, T{});
+    return BoundaryCondition<T>(img, m, b);
+}
+
+// ---------------------------------------------------------------- user DSL programs (float configs)
+// C2: float local operator over the non-zero domain taps, row-major order
+class DomReduceF : public Kernel<float> {
+    Accessor<float> &in; Domain &dom; Mask<float> &mask; Reduce mode;
+  public:
+    DomReduceF(IterationSpace<float> &is, Accessor<float> &in, Domain &dom, Mask<float> &mask, Reduce mode)
+        : Kernel(is), in(in), dom(dom), mask(mask), mode(mode) { add_accessor(&in); }
+    void kernel() {
+        output() = reduce(dom, mode, [&]() -> float { return mask(dom) * in(dom); });
+    }
+};
+// float convolution over ALL taps (zero taps included)
+class ConvolveF : public Kernel<float> {
+    Accessor<float> &in; Mask<float> &mask; Reduce mode;
+  public:
+    ConvolveF(IterationSpace<float> &is, Accessor<float> &in, Mask<float> &mask, Reduce mode)
+        : Kernel(is), in(in), mask(mask), mode(mode) { add_accessor(&in); }
+    void kernel() {
+        output() = convolve(mask, mode, [&]() -> float { return mask() * in(mask); });
+    }
+};
+// C3: the Bilateral_Filter sample body with float pixels, output p/d
+class BilateralF : public Kernel<float> {
+    Accessor<float> &in; Mask<float> &mask; Domain &dom; int sigma_r;
+  public:
+    BilateralF(IterationSpace<float> &is, Accessor<float> &in, Mask<float> &mask, Domain &dom, int sigma_r)
+        : Kernel(is), in(in), mask(mask), dom(dom), sigma_r(sigma_r) { add_accessor(&in); }
+    void kernel() {
+        float c_r = 0.5f / (sigma_r * sigma_r);
+        float d = 0.0f, p = 0.0f;
+        float center = in();
+        iterate(dom, [&]() -> void {
+            float diff = in(dom) - center;
+            float s = expf(-c_r * diff * diff) * mask(dom);
+            d += s;
+            p += s * in(dom);
+        });
+        output() = p / d;
+    }
+};
+// global reductions (C3): output()=in(), reduce = min / max / sum
+template <int OP>
+class GlobalReduceF : public Kernel<float> {
+    Accessor<float> &in;
+  public:
+    GlobalReduceF(IterationSpace<float> &is, Accessor<float> &in) : Kernel(is), in(in) { add_accessor(&in); }
+    void kernel() { output() = in(); }
+    float reduce(float l, float r) const {
+        if (OP == 0) return l + r;
+        if (OP == 1) return min(l, r);
+        return max(l, r);
+    }
+};
+// C5: pyramid kernels of the sample with float pixels
+class GaussF : public Kernel<float> {
+    Accessor<float> &in; Mask<float> &mask;
+  public:
+    GaussF(IterationSpace<float> &is, Accessor<float> &in, Mask<float> &mask) : Kernel(is), in(in), mask(mask) { add_accessor(&in); }
+    void kernel() { output() = convolve(mask, Reduce::SUM, [&]() { return in(mask) * mask(); }); }
+};
+class CopyF : public Kernel<float> {
+    Accessor<float> &in;
+  public:
+    CopyF(IterationSpace<float> &is, Accessor<float> &in) : Kernel(is), in(in) { add_accessor(&in); }
+    void kernel() { output() = in(); }
+};
+template <int OP>  // 0: a-b  1: a+b  2: a + b/2
+class Binary2F : public Kernel<float> {
+    Accessor<float> &a; Accessor<float> &b;
+  public:
+    Binary2F(IterationSpace<float> &is, Accessor<float> &a, Accessor<float> &b) : Kernel(is), a(a), b(b) { add_accessor(&a); add_accessor(&b); }
+    void kernel() {
+        if (OP == 0) output() = a() - b();
+        else if (OP == 1) output() = a() + b();
+        else output() = a() + b() / 2;
+    }
+};
+// single-tap probe kernel in(dx,dy) (exposes the boundary remap)
+template <typename T>
+class TapProbe : public Kernel<T> {
+    Accessor<T> &in; int dx, dy;
+  public:
+    TapProbe(IterationSpace<T> &is, Accessor<T> &in, int dx, int dy) : Kernel<T>(is), in(in), dx(dx), dy(dy) { this->add_accessor(&in); }
+    void kernel() { this->output() = in(dx, dy); }
+};
+
+template <typename T, int SY, int SX>
+struct MaskHolder {
+    T arr[SY][SX];
+    explicit MaskHolder(const T *flat) { std::memcpy(arr, flat, sizeof(arr)); }
+};
+
+// dispatch a run-time (sx,sy) onto the compile-time Mask<T>(const T(&)[SY][SX]) ctor
+#define DISPATCH_SIZE(SXV, SYV, CALL)                       \
+    do {                                                    \
+        if (SXV == 1 && SYV == 1) { CALL(1, 1); }           \
+        else if (SXV == 3 && SYV == 3) { CALL(3, 3); }      \
+        else if (SXV == 5 && SYV == 5) { CALL(5, 5); }      \
+        else if (SXV == 7 && SYV == 7) { CALL(7, 7); }      \
+        else if (SXV == 9 && SYV == 9) { CALL(9, 9); }      \
+        else if (SXV == 13 && SYV == 13) { CALL(13, 13); }  \
+        else if (SXV == 3 && SYV == 1) { CALL(3, 1); }      \
+        else if (SXV == 1 && SYV == 3) { CALL(1, 3); }      \
+        else if (SXV == 5 && SYV == 1) { CALL(5, 1); }      \
+        else if (SXV == 1 && SYV == 5) { CALL(1, 5); }      \
+        else if (SXV == 5 && SYV == 3) { CALL(5, 3); }      \
+        else if (SXV == 3 && SYV == 5) { CALL(3, 5); }      \
+        else return -1;                                     \
+    } while (0)
+
+template <typename T>
+void copy_out(Image<T> &img, T *out) { std::memcpy(out, img.data(), sizeof(T) * img.width() * img.height()); }
+
+} // namespace
+
+extern "C" {
+
+// -------------------------------------------------------------------- local operators
+// sample GaussianBlur (Gaussian_Blur/src/main.cpp:48-66): uchar, Mask<float>, (uchar)(sum+0.5f)
+int ref_gaussian_u8(const uchar *in, uchar *out, int w, int h, int sx, int sy,
+                    const float *coef, int bmode, const int *roi) {
+    Roi r = make_roi(roi, w, h);
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<uchar> I(w, h, const_cast<uchar *>(in));                            \
+        Image<uchar> O(w, h, out);                                                \
+        Mask<float> mask(mh.arr);                                                 \
+        BoundaryCondition<uchar> bc = make_bc(I, mask, bmode);                    \
+        Accessor<uchar> acc(bc, r.acc_w, r.acc_h, r.acc_ox, r.acc_oy);            \
+        IterationSpace<uchar> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);            \
+        smp_gauss::GaussianBlur k(is, acc, mask);                                 \
+        k.execute();                                                              \
+        copy_out(O, out);                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// user program: float convolve (all taps) / reduce over domain (non-zero taps)
+int ref_local_f32(const float *in, float *out, int w, int h, int sx, int sy,
+                  const float *coef, int use_domain, int mode, int bmode, const int *roi) {
+    Roi r = make_roi(roi, w, h);
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<float> I(w, h, const_cast<float *>(in));                            \
+        Image<float> O(w, h, out);                                                \
+        Mask<float> mask(mh.arr);                                                 \
+        Domain dom(mask);                                                         \
+        BoundaryCondition<float> bc = make_bc(I, mask, bmode);                    \
+        Accessor<float> acc(bc, r.acc_w, r.acc_h, r.acc_ox, r.acc_oy);            \
+        IterationSpace<float> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);            \
+        if (use_domain) { DomReduceF k(is, acc, dom, mask, (Reduce)mode); k.execute(); } \
+        else            { ConvolveF  k(is, acc, mask, (Reduce)mode);      k.execute(); } \
+        copy_out(O, out);                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// sample Sobel (Sobel/src/main.cpp:55-73): uchar -> int, reduce over Domain of an int mask
+int ref_sobel_u8(const uchar *in, int *out, int w, int h, int sx, int sy,
+                 const int *coef, int bmode, const int *roi) {
+    Roi r = make_roi(roi, w, h);
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<int, SY_, SX_> mh(coef);                                       \
+        Image<uchar> I(w, h, const_cast<uchar *>(in));                            \
+        Image<int> O(w, h, out);                                                  \
+        Mask<int> mask(mh.arr);                                                   \
+        Domain dom(mask);                                                         \
+        BoundaryCondition<uchar> bc = make_bc(I, dom, bmode);                     \
+        Accessor<uchar> acc(bc, r.acc_w, r.acc_h, r.acc_ox, r.acc_oy);            \
+        IterationSpace<int> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);              \
+        smp_sobel::Sobel k(is, acc, dom, mask);                                   \
+        k.execute();                                                              \
+        copy_out(O, out);                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// sample SobelCombine (Sobel/src/main.cpp:75-98)
+int ref_sobel_combine(const int *a, const int *b, uchar *out, int w, int h, int norm) {
+    Image<int> A(w, h, const_cast<int *>(a)), B(w, h, const_cast<int *>(b));
+    Image<uchar> O(w, h);
+    Accessor<int> aa(A), ab(B);
+    IterationSpace<uchar> is(O);
+    smp_sobel::SobelCombine k(is, aa, ab, norm);
+    k.execute();
+    copy_out(O, out);
+    return 0;
+}
+
+// sample LaplaceFilter (Laplace/src/main.cpp:50-72): uchar -> uchar, +128 and clamp
+int ref_laplace_u8(const uchar *in, uchar *out, int w, int h, int sx, int sy,
+                   const int *coef, int bmode, const int *roi) {
+    Roi r = make_roi(roi, w, h);
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<int, SY_, SX_> mh(coef);                                       \
+        Image<uchar> I(w, h, const_cast<uchar *>(in));                            \
+        Image<uchar> O(w, h, out);                                                \
+        Mask<int> mask(mh.arr);                                                   \
+        Domain dom(mask);                                                         \
+        BoundaryCondition<uchar> bc = make_bc(I, dom, bmode);                     \
+        Accessor<uchar> acc(bc, r.acc_w, r.acc_h, r.acc_ox, r.acc_oy);            \
+        IterationSpace<uchar> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);            \
+        smp_laplace::LaplaceFilter k(is, acc, dom, mask);                         \
+        k.execute();                                                              \
+        copy_out(O, out);                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// sample Dilate (MAX) / Erode-equivalent (MIN) over a full Domain
+int ref_minmax_u8(const uchar *in, uchar *out, int w, int h, int sx, int sy, int is_max, int bmode) {
+    Image<uchar> I(w, h, const_cast<uchar *>(in));
+    Image<uchar> O(w, h);
+    Domain dom(sx, sy);
+    BoundaryCondition<uchar> bc = make_bc(I, dom, bmode);
+    Accessor<uchar> acc(bc);
+    IterationSpace<uchar> is(O);
+    if (is_max) { smp_dilate::Dilate k(is, acc, dom); k.execute(); }
+    else {
+        struct Erode : public Kernel<uchar> {
+            Accessor<uchar> &in; Domain &dom;
+            Erode(IterationSpace<uchar> &is, Accessor<uchar> &in, Domain &dom) : Kernel(is), in(in), dom(dom) { add_accessor(&in); }
+            void kernel() { output() = reduce(dom, Reduce::MIN, [&]() -> uchar { return in(dom); }); }
+        } k(is, acc, dom);
+        k.execute();
+    }
+    copy_out(O, out);
+    return 0;
+}
+
+// sample BlurFilter (Box_Blur/src/main.cpp:49-66)
+int ref_box_u8(const uchar *in, uchar *out, int w, int h, int sx, int sy, int bmode) {
+    Image<uchar> I(w, h, const_cast<uchar *>(in));
+    Image<uchar> O(w, h);
+    Domain dom(sx, sy);
+    BoundaryCondition<uchar> bc = make_bc(I, dom, bmode);
+    Accessor<uchar> acc(bc);
+    IterationSpace<uchar> is(O);
+    smp_box::BlurFilter k(is, acc, dom, sx, sy);
+    k.execute();
+    copy_out(O, out);
+    return 0;
+}
+
+// sample BilateralFilter (Bilateral_Filter/src/main.cpp:49-77), uchar
+int ref_bilateral_u8(const uchar *in, uchar *out, int w, int h, int size, const float *coef,
+                     int sigma_r, int bmode) {
+    int sx = size, sy = size;
+    const int *roi = nullptr;
+    Roi r = make_roi(roi, w, h);
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<uchar> I(w, h, const_cast<uchar *>(in));                            \
+        Image<uchar> O(w, h, out);                                                \
+        Mask<float> mask(mh.arr);                                                 \
+        Domain dom(mask);                                                         \
+        BoundaryCondition<uchar> bc = make_bc(I, dom, bmode);                     \
+        Accessor<uchar> acc(bc, r.acc_w, r.acc_h, r.acc_ox, r.acc_oy);            \
+        IterationSpace<uchar> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);            \
+        smp_bilateral::BilateralFilter k(is, acc, mask, dom, sigma_r);            \
+        k.execute();                                                              \
+        copy_out(O, out);                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// user program: bilateral with float pixels (C3)
+int ref_bilateral_f32(const float *in, float *out, int w, int h, int size, const float *coef,
+                      int sigma_r, int bmode) {
+    int sx = size, sy = size;
+    const int *roi = nullptr;
+    Roi r = make_roi(roi, w, h);
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<float> I(w, h, const_cast<float *>(in));                            \
+        Image<float> O(w, h, out);                                                \
+        Mask<float> mask(mh.arr);                                                 \
+        Domain dom(mask);                                                         \
+        BoundaryCondition<float> bc = make_bc(I, dom, bmode);                     \
+        Accessor<float> acc(bc, r.acc_w, r.acc_h, r.acc_ox, r.acc_oy);            \
+        IterationSpace<float> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);            \
+        BilateralF k(is, acc, mask, dom, sigma_r);                                \
+        k.execute();                                                              \
+        copy_out(O, out);                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// single tap in(dx,dy) through a BoundaryCondition window (wx,wy)
+int ref_tap_u8(const uchar *in, uchar *out, int w, int h, int dx, int dy, int bmode, int wx, int wy) {
+    Image<uchar> I(w, h, const_cast<uchar *>(in));
+    Image<uchar> O(w, h);
+    Boundary b = (Boundary)bmode;
+    BoundaryCondition<uchar> bc = (b == Boundary::CONSTANT) ? BoundaryCondition<uchar>(I, wx, wy, b, (uchar)0)
+                                                            : BoundaryCondition<uchar>(I, wx, wy, b);
+    Accessor<uchar> acc(bc);
+    IterationSpace<uchar> is(O);
+    TapProbe<uchar> k(is, acc, dx, dy);
+    k.execute();
+    copy_out(O, out);
+    return 0;
+}
+
+// -------------------------------------------------------------------- Harris (sample pipeline, 3x3)
+// Harris_Corner/src/main.cpp:230-305 re-enacted with the sample's own kernel classes.
+// out_dx/out_dy/out_dxy (optional) receive the Gaussian-smoothed structure tensor images.
+int ref_harris_u8(const uchar *input, uchar *corners, int w, int h, float k, float threshold,
+                  short *out_dx, short *out_dy, short *out_dxy) {
+    using namespace smp_harris;
+    const short norm = 16;
+    const uchar coef_xy[3][3] = {{1, 2, 1}, {2, 4, 2}, {1, 2, 1}};
+    const char coef_x[3][3] = {{-1, 0, 1}, {-1, 0, 1}, {-1, 0, 1}};
+    const char coef_y[3][3] = {{-1, -1, -1}, {0, 0, 0}, {1, 1, 1}};
+
+    Image<uchar> in(w, h, const_cast<uchar *>(input));
+    Image<uchar> out(w, h);
+    Image<short> dx(w, h), dy(w, h), dxy(w, h), sx(w, h), sy(w, h), sxy(w, h);
+    Mask<uchar> maskxy(coef_xy);
+    Mask<char> maskx(coef_x), masky(coef_y);
+    Domain domx(maskx), domy(masky);
+
+    IterationSpace<short> iter_dx(dx);
+    BoundaryCondition<uchar> bound_in(in, maskx, Boundary::CLAMP);
+    Accessor<uchar> acc_in(bound_in);
+    smp_harris::Sobel derivx(iter_dx, acc_in, maskx, domx);
+    derivx.execute();
+    IterationSpace<short> iter_dy(dy);
+    smp_harris::Sobel derivy(iter_dy, acc_in, masky, domy);
+    derivy.execute();
+    Accessor<short> acc_dx(dx);
+    IterationSpace<short> iter_sx(sx);
+    Square1 squarex(iter_sx, acc_dx);
+    squarex.execute();
+    Accessor<short> acc_dy(dy);
+    IterationSpace<short> iter_sy(sy);
+    Square1 squarey(iter_sy, acc_dy);
+    squarey.execute();
+    IterationSpace<short> iter_sxy(sxy);
+    Square2 squarexy(iter_sxy, acc_dx, acc_dy);
+    squarexy.execute();
+    BoundaryCondition<short> bound_sx(sx, maskxy, Boundary::CLAMP);
+    Accessor<short> acc_sx(bound_sx);
+    smp_harris::Gaussian gaussx(iter_dx, acc_sx, maskxy, norm);
+    gaussx.execute();
+    BoundaryCondition<short> bound_sy(sy, maskxy, Boundary::CLAMP);
+    Accessor<short> acc_sy(bound_sy);
+    smp_harris::Gaussian gaussy(iter_dy, acc_sy, maskxy, norm);
+    gaussy.execute();
+    IterationSpace<short> iter_dxy(dxy);
+    BoundaryCondition<short> bound_sxy(sxy, maskxy, Boundary::CLAMP);
+    Accessor<short> acc_sxy(bound_sxy);
+    smp_harris::Gaussian gaussxy(iter_dxy, acc_sxy, maskxy, norm);
+    gaussxy.execute();
+    IterationSpace<uchar> iter_out(out);
+    Accessor<short> acc_dxy(dxy);
+    HarrisCorner harris(iter_out, acc_dx, acc_dy, acc_dxy, k, threshold);
+    harris.execute();
+
+    copy_out(out, corners);
+    if (out_dx) copy_out(dx, out_dx);
+    if (out_dy) copy_out(dy, out_dy);
+    if (out_dxy) copy_out(dxy, out_dxy);
+    return 0;
+}
+
+// -------------------------------------------------------------------- interpolation (pyramid path)
+// point kernel output()=in() through an interpolating accessor; imode 1=NN 2=LF (dsl/image.hpp:54-61)
+int ref_interp_f32(const float *in, int w, int h, float *out, int ow, int oh, int imode) {
+    Image<float> I(w, h, const_cast<float *>(in));
+    Image<float> O(ow, oh);
+    Accessor<float> acc(I, (Interpolate)imode);
+    IterationSpace<float> is(O);
+    CopyF k(is, acc);
+    k.execute();
+    copy_out(O, out);
+    return 0;
+}
+
+// -------------------------------------------------------------------- pyramid (C5)
+// Gaussian_Laplacian_Pyramid/src/main.cpp:180-250 with float pixels.  All levels of the
+// Gaussian and Laplacian pyramids after the traversal are packed level after level into
+// out_gaus / out_lap (level l has (w>>l)*(h>>l) floats).  tmp level 0.. likewise if non-null.
+int ref_pyramid_f32(const float *input, int w, int h, int depth, int size, const float *coef,
+                    float *out_gaus, float *out_lap, float *out_tmp) {
+    int sx = size, sy = size;
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<float> gaus(w, h, const_cast<float *>(input));                      \
+        Image<float> tmp(w, h);                                                   \
+        Image<float> lap(w, h);                                                   \
+        Mask<float> mask(mh.arr);                                                 \
+        Pyramid<float> pgaus(gaus, depth), ptmp(tmp, depth), plap(lap, depth);    \
+        traverse(pgaus, ptmp, plap, [&]() {                                       \
+            if (!pgaus.is_top_level()) {                                          \
+                BoundaryCondition<float> bound(pgaus(-1), mask, Boundary::CLAMP); \
+                Accessor<float> acc1(bound);                                      \
+                IterationSpace<float> iter1(ptmp(-1));                            \
+                GaussF blur(iter1, acc1, mask);                                   \
+                blur.execute();                                                   \
+                Accessor<float> acc2(ptmp(-1), Interpolate::NN);                  \
+                IterationSpace<float> iter2(pgaus(0));                            \
+                CopyF sub(iter2, acc2);                                           \
+                sub.execute();                                                    \
+                Accessor<float> acc3(pgaus(-1));                                  \
+                Accessor<float> acc4(pgaus(0), Interpolate::LF);                  \
+                IterationSpace<float> iter3(plap(-1));                            \
+                Binary2F<0> DoG(iter3, acc3, acc4);                               \
+                DoG.execute();                                                    \
+            }                                                                     \
+            traverse();                                                           \
+            if (!pgaus.is_bottom_level()) {                                       \
+                Accessor<float> acc1(pgaus(1), Interpolate::LF);                  \
+                Accessor<float> acc2(plap(0));                                    \
+                IterationSpace<float> iter1(pgaus(0));                            \
+                Binary2F<1> res(iter1, acc1, acc2);                               \
+                res.execute();                                                    \
+                Accessor<float> acc3(plap(1), Interpolate::LF);                   \
+                Accessor<float> acc4(plap(0));                                    \
+                IterationSpace<float> iter2(plap(0));                             \
+                Binary2F<2> blend(iter2, acc3, acc4);                             \
+                blend.execute();                                                  \
+            }                                                                     \
+        });                                                                       \
+        size_t off = 0;                                                           \
+        for (int l = 0; l < depth; ++l) {                                         \
+            Image<float> &g = pgaus(l); Image<float> &p = plap(l); Image<float> &t = ptmp(l); \
+            size_t n = (size_t)g.width() * g.height();                            \
+            if (out_gaus) std::memcpy(out_gaus + off, g.data(), n * sizeof(float)); \
+            if (out_lap)  std::memcpy(out_lap + off, p.data(), n * sizeof(float)); \
+            if (out_tmp)  std::memcpy(out_tmp + off, t.data(), n * sizeof(float)); \
+            off += n;                                                             \
+        }                                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// the sample's own char pyramid (sample classes, sample pipeline) -- pins the float variant's structure
+int ref_pyramid_s8(const char *input, int w, int h, int depth, int size, const float *coef,
+                   char *out_gaus, char *out_lap) {
+    using namespace smp_pyr;
+    int sx = size, sy = size;
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<char> gaus(w, h, const_cast<char *>(input));                        \
+        Image<char> tmp(w, h);                                                    \
+        Image<char> lap(w, h);                                                    \
+        Mask<float> mask(mh.arr);                                                 \
+        Pyramid<char> pgaus(gaus, depth), ptmp(tmp, depth), plap(lap, depth);     \
+        traverse(pgaus, ptmp, plap, [&]() {                                       \
+            if (!pgaus.is_top_level()) {                                          \
+                BoundaryCondition<char> bound(pgaus(-1), mask, Boundary::CLAMP);  \
+                Accessor<char> acc1(bound);                                       \
+                IterationSpace<char> iter1(ptmp(-1));                             \
+                smp_pyr::Gaussian blur(iter1, acc1, mask);                        \
+                blur.execute();                                                   \
+                Accessor<char> acc2(ptmp(-1), Interpolate::NN);                   \
+                IterationSpace<char> iter2(pgaus(0));                             \
+                Subsample sub(iter2, acc2);                                       \
+                sub.execute();                                                    \
+                Accessor<char> acc3(pgaus(-1));                                   \
+                Accessor<char> acc4(pgaus(0), Interpolate::LF);                   \
+                IterationSpace<char> iter3(plap(-1));                             \
+                DifferenceOfGaussian DoG(iter3, acc3, acc4);                      \
+                DoG.execute();                                                    \
+            }                                                                     \
+            traverse();                                                           \
+            if (!pgaus.is_bottom_level()) {                                       \
+                Accessor<char> acc1(pgaus(1), Interpolate::LF);                   \
+                Accessor<char> acc2(plap(0));                                     \
+                IterationSpace<char> iter1(pgaus(0));                             \
+                Restore res(iter1, acc1, acc2);                                   \
+                res.execute();                                                    \
+                Accessor<char> acc3(plap(1), Interpolate::LF);                    \
+                Accessor<char> acc4(plap(0));                                     \
+                IterationSpace<char> iter2(plap(0));                              \
+                Blend blend(iter2, acc3, acc4);                                   \
+                blend.execute();                                                  \
+            }                                                                     \
+        });                                                                       \
+        size_t off = 0;                                                           \
+        for (int l = 0; l < depth; ++l) {                                         \
+            Image<char> &g = pgaus(l); Image<char> &p = plap(l);                  \
+            size_t n = (size_t)g.width() * g.height();                            \
+            if (out_gaus) std::memcpy(out_gaus + off, g.data(), n);               \
+            if (out_lap)  std::memcpy(out_lap + off, p.data(), n);                \
+            off += n;                                                             \
+        }                                                                         \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+
+// -------------------------------------------------------------------- global reductions
+// DSL semantics: strict serial row-major left fold (dsl/kernel.hpp:121-151). op 0=sum 1=min 2=max
+int ref_global_reduce_f32(const float *in, int w, int h, int op, const int *roi, float *result) {
+    Roi r = make_roi(roi, w, h);
+    Image<float> I(w, h, const_cast<float *>(in));
+    Image<float> O(w, h);
+    Accessor<float> acc(I, r.is_w, r.is_h, r.is_ox, r.is_oy);
+    IterationSpace<float> is(O, r.is_w, r.is_h, r.is_ox, r.is_oy);
+    if (op == 0) { GlobalReduceF<0> k(is, acc); *result = k.reduced_data(); }
+    else if (op == 1) { GlobalReduceF<1> k(is, acc); *result = k.reduced_data(); }
+    else { GlobalReduceF<2> k(is, acc); *result = k.reduced_data(); }
+    return 0;
+}
+// sample Reduction kernel (Reduction_Sum/src/main.cpp:44-62)
+int ref_sample_reduce_sum_f32(const float *in, int w, int h, float *result) {
+    Image<float> I(w, h, const_cast<float *>(in));
+    Image<float> O(w, h);
+    Accessor<float> acc(I);
+    IterationSpace<float> is(O);
+    smp_redsum::Reduction k(is, acc);
+    k.execute();
+    *result = k.reduced_data();
+    return 0;
+}
+
+} // extern "C"
+
+// reference CPU runtime reduction (runtime/hipacc_cpu_red.hpp:19-68); thread-count dependent
+static inline float rt_sum(float a, float b) { return a + b; }
+static inline float rt_min(float a, float b) { return a < b ? a : b; }
+static inline float rt_max(float a, float b) { return a > b ? a : b; }
+REDUCTION_CPU_2D(rtSum, float, rt_sum, 1)
+REDUCTION_CPU_2D(rtMin, float, rt_min, 1)
+REDUCTION_CPU_2D(rtMax, float, rt_max, 1)
+
+extern "C" {
+int ref_rt_reduce_f32(const float *in, int w, int h, int stride, int op, int ox, int oy, float *result) {
+    float *p = const_cast<float *>(in);
+    if (op == 0) *result = rtSumKernel(p, w, h, stride, ox, oy);
+    else if (op == 1) *result = rtMinKernel(p, w, h, stride, ox, oy);
+    else *result = rtMaxKernel(p, w, h, stride, ox, oy);
+    return 0;
+}
+
+// -------------------------------------------------------------------- the samples' embedded plain-C checkers
+// (interior pixels only; these are what the reference's own tests compare against)
+int ref_sample_gaussian_filter(const uchar *in, uchar *out, const float *filter, int sx, int sy, int w, int h) {
+    smp_gauss::gaussian_filter(const_cast<uchar *>(in), out, const_cast<float *>(filter), sx, sy, w, h);
+    return 0;
+}
+int ref_sample_laplace_filter(const uchar *in, uchar *out, const int *filter, int size, int w, int h) {
+    smp_laplace::laplace_filter(const_cast<uchar *>(in), out, const_cast<int *>(filter), size, w, h);
+    return 0;
+}
+int ref_sample_sobel_filter(const uchar *in, int *out, const int *filter, int sx, int sy, int w, int h) {
+    smp_sobel::sobel_filter(const_cast<uchar *>(in), out, const_cast<int *>(filter), sx, sy, w, h);
+    return 0;
+}
+int ref_sample_sobel_combine(const int *a, const int *b, uchar *out, int w, int h, int norm) {
+    smp_sobel::sobel_combine(const_cast<int *>(a), const_cast<int *>(b), out, w, h, norm);
+    return 0;
+}
+int ref_sample_bilateral_filter(const uchar *in, uchar *out, const float *filter, int sigma_s, int sigma_r, int w, int h) {
+    smp_bilateral::bilateral_filter(const_cast<uchar *>(in), out, const_cast<float *>(filter), sigma_s, sigma_r, w, h);
+    return 0;
+}
+int ref_sample_reduction(const float *in, float *out, int w, int h) {
+    *out = 0.0f;
+    smp_redsum::reduction(const_cast<float *>(in), out, w, h);
+    return 0;
+}
+} // extern "C"
