@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 operator path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--extra]
+
+Workload (BASELINE.json configs[1], "C2"): Sobel-X + Sobel-Y + Laplace 3x3 local operators on a float
+8192 x 8192 image with MIRROR boundary handling.  One step = the three operators over the image (three
+launches of the tiled local-operator kernel).  value = operator-pixels per second: 3 * 8192 * 8192
+pixels per step / step time, whole job.  N > 1 (torchrun, one rank per GPU): weak scaling -- every rank
+owns an 8192 x 8192 row strip of an 8192 x (8192*N) image, ghost rows are exchanged with the
+neighbouring ranks inside the timed step (NCCL send/recv), MIRROR is applied only at the global edges.
+
+Timed on the device with CUDA events on the stream the kernels run on, after W >= 3 warm-up steps,
+barrier + synchronize on both sides, max over ranks.  Inputs (256 MiB) and outputs (768 MiB) are
+larger than the 126 MB L2, so no explicit flush is needed (stated in `config`).
+
+--impl reference: the reference's CPU path for the same workload (the restated -emit-cpu code in
+oracle/, all host threads; the Hipacc compiler itself cannot be built here -- DESIGN.md) on a bounded
+sample.  Rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W = H = 8192
+OPS = ("sobel_x", "sobel_y", "laplace")
+ALG_BYTES_PER_PX = 8            # 4 B read + 4 B write per pixel per operator
+METRIC = "Gpixels/s per operator (local operators Sobel-X + Sobel-Y + Laplace 3x3, float 8192x8192, MIRROR)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.1)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def specs_for_workload():
+    import numpy as np
+    from hipacc_b200 import _abi as A, masks as M, specs as S
+    return [S.domain_reduce_f32(m.astype(np.float32), A.MIRROR) for m in (M.SOBEL3_X, M.SOBEL3_Y, M.LAPLACE3)]
+
+
+# --------------------------------------------------------------------------------------- CPU legs
+def cpu_baseline(rows, repeats=3):
+    """The oracle ("port" of -emit-cpu, oracle/emit_cpu.cpp) on the host cores: the three operators on a
+    W x rows sample of the same synthetic image.  Returns (Gpx/s, cores, sample description)."""
+    import numpy as np
+    from hipacc_b200 import synth
+    from oracle import oracle as O
+    img = synth.image_np("float32", W, rows, seed=2)
+    specs = specs_for_workload()
+    outs = [np.empty_like(img) for _ in specs]
+    for s, o in zip(specs, outs):   # warm-up (page faults, OpenMP pool)
+        O.local_op(s, img, out=o)
+    best = float("inf")
+    for _ in range(repeats):
+        t = time.perf_counter()
+        for s, o in zip(specs, outs):
+            O.local_op(s, img, out=o)
+        best = min(best, time.perf_counter() - t)
+    return len(specs) * W * rows / best / 1e9, O.num_threads(), f"3 operators on {W}x{rows} float rows of the same image, best of {repeats}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    import numpy as np
+    from hipacc_b200 import synth
+    from oracle import oracle as O
+    rows = 4096   # bounded sample: half of the image per step
+    img = synth.image_np("float32", W, rows, seed=2)
+    specs = specs_for_workload()
+    outs = [np.empty_like(img) for _ in specs]
+
+    def step():
+        for s, o in zip(specs, outs):
+            O.local_op(s, img, out=o)
+    for _ in range(warm):
+        step()
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t) / steps
+    val = len(specs) * W * rows / dt / 1e9
+    cores = O.num_threads()
+    sample = f"{W}x{rows} float rows per step (half of the 8192x8192 image), restated -emit-cpu code, OpenMP {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gpixels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: Sobel-X + Sobel-Y + Laplace 3x3 float 8192x8192 MIRROR (CPU sample)", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Gpixels/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--extra", action="store_true", help="also time the other BASELINE configs (C1, C3, C4 strip, C5) into 'operators'")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import hipacc_b200 as hb
+    from hipacc_b200 import _abi as A, strips, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    hb.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- data: this rank's strip of the global 8192 x (8192*world) image, resident in HBM
+    plan = strips.StripPlan(W, H * world, world, rank, radius=1, boundary=A.MIRROR)
+    plan.validate()
+    stride = (W + 63) // 64 * 64
+    buf = torch.empty((plan.buffer_rows, stride), dtype=torch.float32, device=dev)
+    strips.owned(buf, plan)[:, :W] = synth.image_torch("float32", W, plan.rows, seed=2, y0=plan.y0, device=dev)
+    src = buf[:, :W]
+    outs = [hb.empty_image(A.F32, W, plan.buffer_rows, device=dev) for _ in OPS]
+    specs = specs_for_workload()
+    roi, ghost = plan.roi(), plan.ghost()
+    stream = torch.cuda.current_stream()
+
+    def step():
+        strips.exchange_halos(buf, plan)            # ghost rows from the neighbours (no-op at N = 1)
+        for s, o in zip(specs, outs):
+            hb.local_op(s, src, dst=o, roi_in=roi, roi_out=roi, ghost=ghost, stream=stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = hb.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = hb.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    ms_per_step = ms / steps
+    px_per_step = len(OPS) * W * plan.rows * world      # whole job
+    value = px_per_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (local_tiled_kernel<float,float,float,3,3,0>): per-launch average
+    per_launch_ms = ms / (steps * len(OPS))
+    peak, peak_src = peaks()
+    achieved = ALG_BYTES_PER_PX * W * plan.rows / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "local_tiled_kernel<float,float,float,3,3,0>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ALG_BYTES_PER_PX * W * plan.rows, "avg_launch_ms": per_launch_ms}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("local_tiled_f32_3x3_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the same step through the C-ABI memory calls with HOST (pinned) buffers, copies inside the timed region
+    L = hb.lib()
+    import ctypes as C
+    h_in = torch.empty((plan.rows, W), dtype=torch.float32, pin_memory=True)
+    h_in.copy_(strips.owned(buf, plan)[:, :W])
+    h_out = [torch.empty((plan.rows, W), dtype=torch.float32, pin_memory=True) for _ in OPS]
+    own_in = hb.view(strips.owned(buf, plan)[:, :W])
+    own_out = [hb.view(o[plan.ghost_top:plan.ghost_top + plan.rows]) for o in outs]
+    sp = hb.stream_ptr(stream)
+
+    def e2e_step():
+        L.hb_image_write(C.byref(own_in), C.c_void_p(h_in.data_ptr()), sp)       # host -> HBM (blocking, like hipaccWriteMemory)
+        step()
+        for v, h in zip(own_out, h_out):
+            L.hb_image_read(C.byref(v), C.c_void_p(h.data_ptr()), sp)            # HBM -> host (blocking, like hipaccReadMemory)
+    e2e_steps = max(2, min(steps, 5))
+    e2e_step()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e3.record(stream)
+    sync_all()
+    e2e_s = e2.elapsed_time(e3) * 1e-3 / e2e_steps
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e = {"value": px_per_step / float(t_e.item()) / 1e9, "unit": "Gpixels/s", "h2d_bytes_per_step": 4 * W * plan.rows * world,
+           "d2h_bytes_per_step": 4 * W * plan.rows * len(OPS) * world, "ms_per_step": float(t_e.item()) * 1e3,
+           "api": "hb_image_write + 3 x hb_local_op + 3 x hb_image_read (pinned host buffers)"}
+
+    operators = extra_operators(hb, dev, peak) if (args.extra and world == 1) else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample = cpu_baseline(rows=4096)
+        cpu = {"value": v, "unit": "Gpixels/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gpixels/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "C2: Sobel-X + Sobel-Y + Laplace 3x3 local operators, float 8192x8192 per GPU, MIRROR boundary",
+                       "pixels_per_step": px_per_step, "operators_per_step": len(OPS), "image": f"{W}x{plan.rows} per rank, {W}x{H * world} global",
+                       "l2": "inputs 256 MiB + outputs 768 MiB per step exceed the 126 MB L2; no explicit flush",
+                       "halo_exchange": "none (N=1)" if world == 1 else "1 ghost row per side per step via NCCL send/recv inside the timed region"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if operators:
+            line["operators"] = operators
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_operators(hb, dev, peak):
+    """Gpixels/s and HBM fraction of the other BASELINE.json configs on one GPU (kernel-only, CUDA events)."""
+    import numpy as np
+    import torch
+    from hipacc_b200 import _abi as A, masks as M, specs as S, synth
+    stream = torch.cuda.current_stream()
+    res = {}
+
+    def timeit(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def entry(name, px, alg_bytes, ms, note=""):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        res[name] = {"Gpx_s": px / (ms * 1e-3) / 1e9, "ms": ms, "alg_GB_s": gbs, "hbm_frac": gbs / peak, "note": note}
+
+    # C1 Gaussian 5x5 uchar 4096^2 CLAMP
+    u = hb.empty_image(A.U8, 4096, 4096, device=dev)
+    u.copy_(synth.image_torch("uint8", 4096, 4096, seed=1, device=dev))
+    uo = hb.empty_image(A.U8, 4096, 4096, device=dev)
+    g5 = S.gaussian_blur(M.GAUSS5, A.CLAMP)
+    entry("C1_gaussian5x5_u8_4096", 4096 * 4096, 2 * 4096 * 4096, timeit(lambda: hb.local_op(g5, u, dst=uo, stream=stream)),
+          "bit-exact float mask: FP32-issue bound, 16 MiB image fits L2")
+    # C3 bilateral 13x13 float 8192^2 + fused min/max/sum
+    f = hb.empty_image(A.F32, 8192, 8192, device=dev)
+    f.copy_(synth.image_torch("float32", 8192, 8192, seed=3, scale=255.0, device=dev))
+    fo = hb.empty_image(A.F32, 8192, 8192, device=dev)
+    cm = M.bilateral_mask(13)
+    entry("C3_bilateral13x13_f32_8192", 8192 * 8192, 8 * 8192 * 8192, timeit(lambda: hb.bilateral(f, 13, cm, 16, A.MIRROR, dst=fo, stream=stream), reps=3, warm=1),
+          "169 ex2 per pixel: MUFU/FP32-issue bound")
+    part = torch.zeros(4, dtype=torch.float32, device=dev)
+    entry("C3_reduce_minmaxsum_f32_8192", 8192 * 8192, 4 * 8192 * 8192, timeit(lambda: hb.reduce_minmaxsum_async(fo, part, stream=stream)),
+          "fused min+max+sum, one pass")
+    # C2 single operators
+    for nm, m in (("sobel_x", M.SOBEL3_X), ("laplace", M.LAPLACE3)):
+        sp = S.domain_reduce_f32(m.astype(np.float32), A.MIRROR)
+        entry(f"C2_{nm}_f32_8192", 8192 * 8192, 8 * 8192 * 8192, timeit(lambda: hb.local_op(sp, f, dst=fo, stream=stream)))
+    del f, fo
+    # C4 Harris fused, one 32768 x 4096 strip (the per-GPU share at 8 GPUs)
+    hs = hb.empty_image(A.U8, 32768, 4096, device=dev)
+    hs.copy_(synth.image_torch("uint8", 32768, 4096, seed=4, device=dev))
+    ho = hb.empty_image(A.U8, 32768, 4096, device=dev)
+    entry("C4_harris_fused_u8_32768x4096", 32768 * 4096, 2 * 32768 * 4096, timeit(lambda: hb.harris(hs, dst=ho, stream=stream), reps=5),
+          "fused 9-kernel pipeline, integer-issue bound")
+    del hs, ho
+    # C5 pyramid 8 levels float 16384^2
+    base = hb.empty_image(A.F32, 16384, 16384, device=dev)
+    base.copy_(synth.image_torch("float32", 16384, 16384, seed=5, device=dev))
+    pg = hb.Pyramid(base, 8)
+    pl = hb.Pyramid(hb.empty_image(A.F32, 16384, 16384, device=dev).zero_(), 8)
+    ms = timeit(lambda: hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream), reps=3, warm=1)
+    n = 16384 * 16384
+    entry("C5_pyramid8_f32_16384", n, int(23 * n * 4 / 3), ms, "fused down (blur+subsample, DoG) 9n + fused up 14n bytes per transition")
+    return res
+
+
+if __name__ == "__main__":
+    main()

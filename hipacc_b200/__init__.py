@@ -1,0 +1,258 @@
+"""hipacc_b200 -- B200-native execution path for Hipacc operators.
+
+The product is the C-ABI shared library ``hipacc_b200/lib/libhipacc_b200.so`` (hand-written
+sm_100a CUDA kernels behind include/hipacc_b200.h).  This package is the thin Python host side
+used by the tests and bench.py: it loads the library with ctypes and wraps device buffers
+(torch tensors are used only as HBM allocations / streams -- plumbing, not compute).
+
+There is NO CPU fallback: ``lib()`` raises if the CUDA library has not been built, and every
+operator returns an error status (raised as HbError) when no device kernel exists.
+"""
+import ctypes as C
+import os
+
+from . import _abi as A
+from . import masks, specs, synth  # noqa: F401  (re-exported)
+from ._abi import *  # noqa: F401,F403  (enum constants)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhipacc_b200.so")
+_lib = None
+
+
+class HbError(RuntimeError):
+    def __init__(self, status, what, detail=""):
+        super().__init__(f"{what} failed with status {status}: {detail}")
+        self.status = status
+
+
+def lib():
+    """Load libhipacc_b200.so (once).  Fails loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m hipacc_b200.build` "
+                "(hipacc_b200 has no CPU or PyTorch fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.hb_last_error.restype = C.c_char_p
+        L.hb_last_kernel_ms.restype = C.c_float
+        L.hb_launch_count.restype = C.c_longlong
+        L.hb_local_op.argtypes = [C.POINTER(A.hb_local_desc), C.c_void_p]
+        L.hb_bilateral.argtypes = [C.POINTER(A.hb_bilateral_desc), C.c_void_p]
+        L.hb_point_op.argtypes = [C.POINTER(A.hb_point_desc), C.c_void_p]
+        L.hb_reduce.argtypes = [C.POINTER(A.hb_view), C.c_int, C.c_void_p, C.c_void_p]
+        L.hb_reduce_minmaxsum_f32.argtypes = [C.POINTER(A.hb_view), C.POINTER(C.c_float), C.c_void_p]
+        L.hb_reduce_minmaxsum_f32_async.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
+        L.hb_harris.argtypes = [C.POINTER(A.hb_harris_desc), C.c_void_p]
+        L.hb_pyr_down.argtypes = [C.POINTER(A.hb_pyr_down_desc), C.c_void_p]
+        L.hb_pyr_up.argtypes = [C.POINTER(A.hb_pyr_up_desc), C.c_void_p]
+        L.hb_image_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(A.hb_view)]
+        L.hb_image_destroy.argtypes = [C.POINTER(A.hb_view)]
+        L.hb_image_wrap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(A.hb_view)]
+        L.hb_image_write.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
+        L.hb_image_read.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
+        L.hb_image_copy.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
+        L.hb_image_copy_region.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
+        L.hb_stream_synchronize.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise HbError(rc, what, (lib().hb_last_error() or b"").decode(errors="replace"))
+
+
+def init(device=0):
+    _check(lib().hb_init(int(device)), "hb_init")
+
+
+def set_timing(on):
+    lib().hb_set_timing(1 if on else 0)
+
+
+def last_kernel_ms():
+    return float(lib().hb_last_kernel_ms())
+
+
+def launch_count():
+    return int(lib().hb_launch_count())
+
+
+# ----------------------------------------------------------------------------- torch plumbing
+_TORCH_DTYPES = None
+
+
+def _torch_dtype_map():
+    global _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        import torch
+        _TORCH_DTYPES = {torch.uint8: A.U8, torch.int8: A.S8, torch.int16: A.S16, torch.int32: A.S32,
+                         torch.float32: A.F32}
+    return _TORCH_DTYPES
+
+
+def torch_dtype(dt):
+    import torch
+    return {A.U8: torch.uint8, A.S8: torch.int8, A.S16: torch.int16, A.S32: torch.int32, A.F32: torch.float32}[dt]
+
+
+def view(t, roi=None, ghost=(0, 0)):
+    """hb_view over a 2-D CUDA tensor (row stride may exceed the width; unit pixel stride)."""
+    assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1, "need a 2-D CUDA tensor with contiguous rows"
+    return A.make_view(t.data_ptr(), _torch_dtype_map()[t.dtype], t.shape[1], t.shape[0], t.stride(0), roi, ghost)
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def empty_image(dtype, width, height, device="cuda", align_bytes=256):
+    """Allocate an image in HBM whose rows start on `align_bytes` boundaries (returns the w x h view)."""
+    import torch
+    es = A.DTYPE_SIZE[dtype]
+    per = max(1, align_bytes // es)
+    stride = (width + per - 1) // per * per
+    buf = torch.empty((height, stride), dtype=torch_dtype(dtype), device=device)
+    return buf[:, :width]
+
+
+# ----------------------------------------------------------------------------- operators
+def local_op(spec, src, dst=None, roi_in=None, roi_out=None, ghost=(0, 0), stream=None):
+    """Run a local operator (specs.LocalSpec) on CUDA tensors through hb_local_op."""
+    import torch
+    if dst is None:
+        dst = torch.zeros(src.shape, dtype=torch_dtype(spec.out_dtype), device=src.device)
+    d = A.hb_local_desc()
+    spec.fill(d)
+    d.in_ = view(src, roi_in, ghost)
+    d.out = view(dst, roi_out)
+    _check(lib().hb_local_op(C.byref(d), stream_ptr(stream)), "hb_local_op")
+    return dst
+
+
+def bilateral(src, size, coef, sigma_r, boundary=A.CLAMP, const=0.0, dst=None, stream=None):
+    import numpy as np
+    import torch
+    if dst is None:
+        dst = torch.zeros_like(src)
+    c = np.ascontiguousarray(coef, dtype=np.float32)
+    d = A.hb_bilateral_desc()
+    d.in_, d.out = view(src), view(dst)
+    d.size, d.coef_f32, d.sigma_r = size, c.ctypes.data_as(C.POINTER(C.c_float)), int(sigma_r)
+    d.boundary, d.boundary_const = boundary, float(const)
+    _check(lib().hb_bilateral(C.byref(d), stream_ptr(stream)), "hb_bilateral")
+    return dst
+
+
+def point_op(op, inputs, out_dtype=None, out_shape=None, interp=None, p=(0.0, 0.0), dst=None, stream=None):
+    import torch
+    if dst is None:
+        shape = tuple(out_shape) if out_shape is not None else tuple(inputs[0].shape)
+        dst = torch.zeros(shape, dtype=torch_dtype(out_dtype), device=inputs[0].device)
+    d = A.hb_point_desc()
+    d.n_in = len(inputs)
+    for i, t in enumerate(inputs):
+        d.in_[i] = view(t)
+        d.interp[i] = interp[i] if interp else A.INTERP_NO
+    d.out = view(dst)
+    d.op = op
+    d.p[0], d.p[1] = float(p[0]), float(p[1])
+    _check(lib().hb_point_op(C.byref(d), stream_ptr(stream)), "hb_point_op")
+    return dst
+
+
+def reduce_minmaxsum(src, roi=None, stream=None):
+    """Fused one-pass global reduction of an f32 image -> (min, max, sum) as Python floats (blocking)."""
+    v = view(src, roi)
+    out = (C.c_float * 3)()
+    _check(lib().hb_reduce_minmaxsum_f32(C.byref(v), out, stream_ptr(stream)), "hb_reduce_minmaxsum_f32")
+    return float(out[0]), float(out[1]), float(out[2])
+
+
+def reduce_minmaxsum_async(src, partials, roi=None, stream=None):
+    """Leave {float min, float max, double sum} in `partials` (a 16-byte CUDA buffer) without syncing."""
+    v = view(src, roi)
+    _check(lib().hb_reduce_minmaxsum_f32_async(C.byref(v), C.c_void_p(partials.data_ptr()), stream_ptr(stream)),
+           "hb_reduce_minmaxsum_f32_async")
+
+
+def reduce(src, mode, roi=None, stream=None):
+    import numpy as np
+    v = view(src, roi)
+    res = np.zeros(1, dtype=A.DTYPE_NUMPY[v.dtype])
+    _check(lib().hb_reduce(C.byref(v), mode, res.ctypes.data_as(C.c_void_p), stream_ptr(stream)), "hb_reduce")
+    return res[0]
+
+
+def harris(src, k=masks.HARRIS_K, threshold=masks.HARRIS_THRESHOLD, dst=None, stream=None):
+    """Fused Harris corner detector (uchar -> uchar), one kernel (hb_harris)."""
+    import torch
+    if dst is None:
+        dst = torch.zeros_like(src)
+    d = A.hb_harris_desc()
+    d.in_, d.out = view(src), view(dst)
+    d.k, d.threshold = float(k), float(threshold)
+    _check(lib().hb_harris(C.byref(d), stream_ptr(stream)), "hb_harris")
+    return dst
+
+
+def harris_unfused(src, k=masks.HARRIS_K, threshold=masks.HARRIS_THRESHOLD, stream=None):
+    """The sample's nine-kernel pipeline (Harris_Corner/src/main.cpp:230-305) through the generic
+    local / point operators -- the shape Hipacc's rewritten host code has; used to cross-check the
+    fused kernel and to measure what fusion buys."""
+    dx = local_op(specs.harris_deriv(masks.HARRIS_DX), src, stream=stream)
+    dy = local_op(specs.harris_deriv(masks.HARRIS_DY), src, stream=stream)
+    sx = point_op(A.POINT_SQUARE, [dx], A.S16, stream=stream)
+    sy = point_op(A.POINT_SQUARE, [dy], A.S16, stream=stream)
+    sxy = point_op(A.POINT_MUL, [dx, dy], A.S16, stream=stream)
+    gx = local_op(specs.harris_gauss(masks.HARRIS_GAUSS3), sx, stream=stream)
+    gy = local_op(specs.harris_gauss(masks.HARRIS_GAUSS3), sy, stream=stream)
+    gxy = local_op(specs.harris_gauss(masks.HARRIS_GAUSS3), sxy, stream=stream)
+    out = point_op(A.POINT_HARRIS, [gx, gy, gxy], A.U8, p=(k, threshold), stream=stream)
+    return out, gx, gy, gxy
+
+
+class Pyramid:
+    """Device-resident image pyramid: level l is (w >> l) x (h >> l) (hipaccCreatePyramid,
+    runtime/hipacc_cu.tpp:482-497); level 0 aliases the user image like the emitted code."""
+
+    def __init__(self, base, depth):
+        import torch
+        self.depth = depth
+        sizes = specs.pyramid_sizes(base.shape[1], base.shape[0], depth)
+        self.levels = [base] + [empty_image(A.F32, w, h, device=base.device).zero_() for (w, h) in sizes[1:]]
+        assert base.dtype == torch.float32
+
+
+def pyr_down(fine, coarse, mask, lap_fine=None, tmp=None, stream=None):
+    import numpy as np
+    m = np.ascontiguousarray(mask, dtype=np.float32)
+    d = A.hb_pyr_down_desc()
+    d.fine, d.coarse = view(fine), view(coarse)
+    if tmp is not None:
+        d.tmp = view(tmp)
+    if lap_fine is not None:
+        d.lap_fine = view(lap_fine)
+    d.size, d.coef_f32 = m.shape[0], m.ctypes.data_as(C.POINTER(C.c_float))
+    _check(lib().hb_pyr_down(C.byref(d), stream_ptr(stream)), "hb_pyr_down")
+
+
+def pyr_up(coarse_gaus, coarse_lap, fine_gaus, fine_lap, stream=None):
+    d = A.hb_pyr_up_desc()
+    d.coarse_gaus, d.coarse_lap, d.fine_gaus, d.fine_lap = view(coarse_gaus), view(coarse_lap), view(fine_gaus), view(fine_lap)
+    _check(lib().hb_pyr_up(C.byref(d), stream_ptr(stream)), "hb_pyr_up")
+
+
+def pyramid_traverse(pgaus, plap, mask, ptmp=None, stream=None):
+    """The traversal of Gaussian_Laplacian_Pyramid/src/main.cpp:199-248: way down builds the Gaussian and
+    Laplacian pyramids, way up restores / blends.  Host recursion only (dsl/pyramid.hpp:182-208)."""
+    depth = pgaus.depth
+    for l in range(1, depth):
+        pyr_down(pgaus.levels[l - 1], pgaus.levels[l], mask, lap_fine=plap.levels[l - 1],
+                 tmp=None if ptmp is None else ptmp.levels[l - 1], stream=stream)
+    for l in range(depth - 2, -1, -1):
+        pyr_up(pgaus.levels[l + 1], plap.levels[l + 1], pgaus.levels[l], plap.levels[l], stream=stream)

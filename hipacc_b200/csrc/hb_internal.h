@@ -1,0 +1,59 @@
+// hb_internal.h -- host-side plumbing shared by the translation units of libhipacc_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/hipacc_b200.h"
+
+namespace hb {
+
+void log_msg(int level, const char *fmt, ...);
+void set_last_error(const std::string &s);
+extern std::atomic<long long> g_launches;
+extern bool g_timing;
+
+// checkErr of the reference (runtime/hipacc_cu.hpp:69-75): log and continue, but also report a status
+inline int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return HB_OK;
+    log_msg(2, "ERROR: %s (%d): %s: %s", what, (int)e, cudaGetErrorName(e), cudaGetErrorString(e));
+    return HB_ERR_CUDA;
+}
+
+// Brackets one operator call with events when hb_set_timing(1) (the reference's print_timing,
+// runtime/hipacc_cu_standalone.hpp:297-326), and checks the launch.
+struct OpScope {
+    cudaStream_t stream;
+    const char *name;
+    OpScope(cudaStream_t s, const char *n);
+    int finish();  // returns status of the launches issued inside the scope
+};
+
+inline hb_view norm_view(const hb_view &v) {
+    hb_view o = v;
+    if (o.width <= 0 || o.height <= 0) { o.width = o.img_width; o.height = o.img_height; o.offset_x = 0; o.offset_y = 0; }
+    return o;
+}
+inline int dtype_size(int dt) {
+    switch (dt) { case HB_U8: case HB_S8: return 1; case HB_U16: case HB_S16: return 2; default: return 4; }
+}
+inline bool view_ok(const hb_view &v) {
+    return v.data && v.img_width > 0 && v.img_height > 0 && v.stride >= v.img_width && v.dtype >= HB_U8 && v.dtype <= HB_F32 &&
+           v.offset_x >= 0 && v.offset_y >= 0 && v.offset_x + v.width <= v.img_width && v.offset_y + v.height <= v.img_height &&
+           v.ghost_top >= 0 && v.ghost_bottom >= 0 && v.offset_y - v.ghost_top >= 0 &&
+           v.offset_y + v.height + v.ghost_bottom <= v.img_height;
+}
+
+int sm_count();
+
+}  // namespace hb
+
+#define HB_REQUIRE(cond, status, ...)                       \
+    do {                                                    \
+        if (!(cond)) {                                      \
+            hb::log_msg(2, __VA_ARGS__);                    \
+            return (status);                                \
+        }                                                   \
+    } while (0)

@@ -1,0 +1,320 @@
+// hb_local.cu -- local-operator engine (tiled 2-D stencils) for sm_100a.
+//
+// Replaces the generated local-operator kernels of Hipacc's CUDA backend (kernel text
+// lib/Rewrite/Rewrite.cpp:2726-2883, body lib/AST/ASTTranslate.cpp:510-1197; one pixel per
+// thread, per-block `goto` border variants) -- paths relative to the Hipacc tree.
+//
+// Design (DESIGN.md section "Local-operator engine"):
+//   * one CTA = one 128 x 32 output tile; the input tile + halo is staged ONCE into shared
+//     memory, already converted to the accumulation type, so the boundary mode is a property of
+//     the loader only: interior tiles take a branch-free 16-byte vector path, border tiles the
+//     remapping path; the compute loop is identical and branch-free for both.
+//   * each thread owns 4 adjacent pixels x 4 rows (register blocking); it walks the input rows
+//     once (row-stationary): every staged row is read from shared memory with 16-byte loads and
+//     feeds all output rows it contributes to.  Per output pixel taps are still folded in
+//     row-major order, so results are bit-identical to the DSL's sequential fold.
+//   * mask coefficients live in the kernel parameter (constant) bank and the tap loops are fully
+//     unrolled for 3x3 / 5x5 / 7x7; other sizes use the generic kernel below.
+#include "hb_common.cuh"
+#include "hb_internal.h"
+
+#include <cstring>
+
+namespace hb {
+
+constexpr int kMaxTaps = 169;  // up to 13 x 13
+
+struct LocalParams {
+    const void *in;
+    void *out;
+    int in_stride, in_iw, in_ih;
+    Window win;
+    int in_ox, in_oy;  // IS-relative (0,0) reads input pixel (in_ox, in_oy)  (dsl/image.hpp:412)
+    int out_stride, out_ox, out_oy, is_w, is_h;
+    int size_x, size_y;
+    int reduce_mode, tap, acc_s16, epilogue;
+    float epi_f[3];
+    int epi_i[3];
+    float cval_f;
+    int cval_i;
+    unsigned dom[6];  // bit k: tap k (row-major) is visited
+    union {
+        float f[kMaxTaps];
+        int i[kMaxTaps];
+    } coef;
+};
+
+// ---- arithmetic in the accumulation type (float: separately rounded mul / add) ----
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ int mul_rn(int a, int b) { return a * b; }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ int add_rn(int a, int b) { return a + b; }
+
+template <typename TS> __device__ __forceinline__ TS fold_identity(int mode);
+template <> __device__ __forceinline__ float fold_identity<float>(int mode) {
+    return mode == HB_REDUCE_SUM ? 0.0f : mode == HB_REDUCE_PROD ? 1.0f : mode == HB_REDUCE_MIN ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+}
+template <> __device__ __forceinline__ int fold_identity<int>(int mode) {
+    return mode == HB_REDUCE_SUM ? 0 : mode == HB_REDUCE_PROD ? 1 : mode == HB_REDUCE_MIN ? 2147483647 : (-2147483647 - 1);
+}
+template <typename TS>
+__device__ __forceinline__ TS fold(TS acc, TS v, int mode) {
+    switch (mode) {
+    case HB_REDUCE_SUM: return add_rn(acc, v);
+    case HB_REDUCE_MIN: return v < acc ? v : acc;  // hipacc::math::min(fun(), result), dsl/kernel.hpp:256
+    case HB_REDUCE_MAX: return v > acc ? v : acc;
+    default: return mul_rn(acc, v);
+    }
+}
+
+template <typename TS> __device__ __forceinline__ TS coef_of(const LocalParams &p, int k);
+template <> __device__ __forceinline__ float coef_of<float>(const LocalParams &p, int k) { return p.coef.f[k]; }
+template <> __device__ __forceinline__ int coef_of<int>(const LocalParams &p, int k) { return p.coef.i[k]; }
+
+template <typename TO>
+__device__ __forceinline__ TO epilogue(float acc, const LocalParams &p) {
+    switch (p.epilogue) {
+    case HB_EPI_ADD_CAST: return cast_out<TO, float>(__fadd_rn(acc, p.epi_f[0]));
+    case HB_EPI_ADD_CLAMP_CAST: {
+        float v = __fadd_rn(acc, p.epi_f[0]);
+        v = v < p.epi_f[2] ? v : p.epi_f[2];
+        v = v > p.epi_f[1] ? v : p.epi_f[1];
+        return cast_out<TO, float>(v);
+    }
+    case HB_EPI_DIVI_CAST: return cast_out<TO, int>(__float2int_rz(acc) / p.epi_i[0]);
+    case HB_EPI_DIVF_CAST: return cast_out<TO, float>(__fdiv_rn(acc, p.epi_f[0]));
+    default: return cast_out<TO, float>(acc);
+    }
+}
+template <typename TO>
+__device__ __forceinline__ TO epilogue(int acc, const LocalParams &p) {
+    if (p.acc_s16) acc = (int)(short)acc;
+    switch (p.epilogue) {
+    case HB_EPI_ADD_CAST: return cast_out<TO, int>(acc + p.epi_i[0]);
+    case HB_EPI_ADD_CLAMP_CAST: {
+        int v = acc + p.epi_i[0];
+        v = min(v, p.epi_i[2]);
+        v = max(v, p.epi_i[1]);
+        return cast_out<TO, int>(v);
+    }
+    case HB_EPI_DIVI_CAST: return cast_out<TO, int>(acc / p.epi_i[0]);
+    case HB_EPI_DIVF_CAST: return cast_out<TO, float>(__fdiv_rn((float)acc, p.epi_f[0]));
+    default: return cast_out<TO, int>(acc);
+    }
+}
+
+template <typename TS> __device__ __forceinline__ TS cval_of(const LocalParams &p);
+template <> __device__ __forceinline__ float cval_of<float>(const LocalParams &p) { return p.cval_f; }
+template <> __device__ __forceinline__ int cval_of<int>(const LocalParams &p) { return p.cval_i; }
+
+// ------------------------------------------------------------------------------------------------
+// Tiled kernel: SX x SY compile-time.  VAR 0: SUM of coef*in (no domain test, hot path).
+//                                        VAR 1: run-time reduce mode / tap kind / domain holes.
+// ------------------------------------------------------------------------------------------------
+constexpr int TW = 128, RPT = 4, BX = 32, BY = 8, TH = BY * RPT;
+
+template <typename TI, typename TS, typename TO, int SX, int SY, int VAR>
+__global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_constant__ LocalParams p) {
+    constexpr int HX = SX / 2, HY = SY / 2;
+    constexpr int HXP = round_up(HX, 4);
+    constexpr int TWS = TW + 2 * HXP;
+    constexpr int ROWS = TH + SY - 1;
+    constexpr int WIN = 4 + 2 * HXP;
+    __shared__ __align__(16) TS tile[ROWS * TWS];
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * BX + tx;
+    const int gx0 = blockIdx.x * TW, gy0 = blockIdx.y * TH;
+
+    stage_tile<TI, TS, ROWS, TWS, BX * BY>(tile, static_cast<const TI *>(p.in), p.in_stride, p.in_iw, p.in_ih, p.win,
+                                           (TI)cval_of<TS>(p), p.in_ox + gx0 - HXP, p.in_oy + gy0 - HY, tid);
+    __syncthreads();
+
+    const int mode = VAR == 0 ? (int)HB_REDUCE_SUM : p.reduce_mode;
+    TS acc[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[r][i] = fold_identity<TS>(mode);
+
+    const int r0 = ty * RPT;
+#pragma unroll
+    for (int ir = 0; ir < RPT + SY - 1; ++ir) {
+        TS w[WIN];
+        const TS *row = tile + (r0 + ir) * TWS + 4 * tx;
+#pragma unroll
+        for (int q = 0; q < WIN / 4; ++q) {
+            TS t[4];
+            load4(row + 4 * q, t);
+            w[4 * q] = t[0]; w[4 * q + 1] = t[1]; w[4 * q + 2] = t[2]; w[4 * q + 3] = t[3];
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int dy = ir - r;
+            if (dy < 0 || dy >= SY) continue;
+#pragma unroll
+            for (int dx = 0; dx < SX; ++dx) {
+                const int k = dy * SX + dx;
+                if (VAR == 1 && !((p.dom[k >> 5] >> (k & 31)) & 1u)) continue;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const TS pix = w[HXP - HX + i + dx];
+                    TS v;
+                    if (VAR == 0 || p.tap == HB_TAP_MUL) v = mul_rn(coef_of<TS>(p, k), pix);
+                    else v = pix;
+                    acc[r][i] = fold<TS>(acc[r][i], v, mode);
+                }
+            }
+        }
+    }
+
+    TO *out = static_cast<TO *>(p.out);
+    const int gx = gx0 + 4 * tx;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int gy = gy0 + r0 + r;
+        if (gy >= p.is_h || gx >= p.is_w) continue;
+        TO o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = epilogue<TO>(acc[r][i], p);
+        TO *dst = out + (size_t)(p.out_oy + gy) * p.out_stride + p.out_ox + gx;
+        if (gx + 3 < p.is_w && (reinterpret_cast<uintptr_t>(dst) % (4 * sizeof(TO)) == 0)) {
+            store4(dst, o);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (gx + i < p.is_w) dst[i] = o[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic kernel: any mask size up to 13x13 (run-time), one pixel per thread, 32 x 8 tile.
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TS, typename TO>
+__global__ void __launch_bounds__(256) local_generic_kernel(const __grid_constant__ LocalParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TS *tile = reinterpret_cast<TS *>(smem_raw);
+    const int sx = p.size_x, sy = p.size_y, hx = sx / 2, hy = sy / 2;
+    const int pw = 32 + sx - 1, ph = 8 + sy - 1;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    const int gx0 = blockIdx.x * 32, gy0 = blockIdx.y * 8;
+    {
+        const TI *in = static_cast<const TI *>(p.in);
+        ImgRef<TI> im{in, p.in_stride, p.in_iw, p.in_ih};
+        const TI cv = (TI)cval_of<TS>(p);
+        const int x_start = p.in_ox + gx0 - hx, y_start = p.in_oy + gy0 - hy;
+        for (int e = tid; e < pw * ph; e += 256) {
+            const int r = e / pw, c = e - r * pw;
+            tile[e] = (TS)fetch_bh(im, p.win, x_start + c, y_start + r, cv);
+        }
+    }
+    __syncthreads();
+    const int gx = gx0 + tx, gy = gy0 + ty;
+    if (gx >= p.is_w || gy >= p.is_h) return;
+    const int mode = p.reduce_mode;
+    TS acc = fold_identity<TS>(mode);
+    for (int dy = 0; dy < sy; ++dy)
+        for (int dx = 0; dx < sx; ++dx) {
+            const int k = dy * sx + dx;
+            if (!((p.dom[k >> 5] >> (k & 31)) & 1u)) continue;
+            const TS pix = tile[(ty + dy) * pw + tx + dx];
+            const TS v = p.tap == HB_TAP_MUL ? mul_rn(coef_of<TS>(p, k), pix) : pix;
+            acc = fold<TS>(acc, v, mode);
+        }
+    static_cast<TO *>(p.out)[(size_t)(p.out_oy + gy) * p.out_stride + p.out_ox + gx] = epilogue<TO>(acc, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TS, typename TO>
+static int launch_local(const LocalParams &p, bool fast, cudaStream_t s) {
+    dim3 block(BX, BY);
+    dim3 grid((p.is_w + TW - 1) / TW, (p.is_h + TH - 1) / TH);
+#define HB_TILED(SXV, SYV)                                                                   \
+    if (p.size_x == SXV && p.size_y == SYV) {                                                \
+        if (fast) local_tiled_kernel<TI, TS, TO, SXV, SYV, 0><<<grid, block, 0, s>>>(p);     \
+        else local_tiled_kernel<TI, TS, TO, SXV, SYV, 1><<<grid, block, 0, s>>>(p);          \
+        g_launches++;                                                                        \
+        return HB_OK;                                                                        \
+    }
+    HB_TILED(3, 3)
+    HB_TILED(5, 5)
+    HB_TILED(7, 7)
+#undef HB_TILED
+    dim3 g2((p.is_w + 31) / 32, (p.is_h + 7) / 8);
+    size_t smem = (size_t)(32 + p.size_x - 1) * (8 + p.size_y - 1) * sizeof(TS);
+    local_generic_kernel<TI, TS, TO><<<g2, dim3(32, 8), smem, s>>>(p);
+    g_launches++;
+    return HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
+    HB_REQUIRE(d, HB_ERR_INVALID, "hb_local_op: null descriptor");
+    hb_view in = norm_view(d->in), out = norm_view(d->out);
+    HB_REQUIRE(view_ok(in) && view_ok(out), HB_ERR_INVALID, "hb_local_op: malformed view");
+    HB_REQUIRE(d->size_x > 0 && d->size_y > 0 && (d->size_x & 1) && (d->size_y & 1) && d->size_x * d->size_y <= kMaxTaps &&
+                   d->size_x <= 13 && d->size_y <= 13,
+               HB_ERR_UNSUPPORTED, "hb_local_op: mask %dx%d unsupported (odd sizes up to 13x13)", d->size_x, d->size_y);
+    HB_REQUIRE(d->tap == HB_TAP_IN || d->coef_f32 || d->coef_s32, HB_ERR_INVALID, "hb_local_op: HB_TAP_MUL needs coefficients");
+    HB_REQUIRE(d->reduce_mode >= HB_REDUCE_SUM && d->reduce_mode <= HB_REDUCE_PROD, HB_ERR_INVALID, "hb_local_op: bad reduce mode");
+    HB_REQUIRE(d->boundary >= HB_BOUNDARY_UNDEFINED && d->boundary <= HB_BOUNDARY_CONSTANT, HB_ERR_INVALID, "hb_local_op: bad boundary mode");
+
+    LocalParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in.data; p.out = out.data;
+    p.in_stride = in.stride; p.in_iw = in.img_width; p.in_ih = in.img_height;
+    p.win = Window{in.offset_x, in.offset_x + in.width, in.offset_y - in.ghost_top, in.offset_y + in.height + in.ghost_bottom, d->boundary};
+    p.in_ox = in.offset_x; p.in_oy = in.offset_y;
+    p.out_stride = out.stride; p.out_ox = out.offset_x; p.out_oy = out.offset_y; p.is_w = out.width; p.is_h = out.height;
+    p.size_x = d->size_x; p.size_y = d->size_y;
+    p.reduce_mode = d->reduce_mode; p.tap = d->tap; p.acc_s16 = d->acc_dtype == HB_S16; p.epilogue = d->epilogue;
+    for (int i = 0; i < 3; ++i) { p.epi_f[i] = (float)d->epi_p[i]; p.epi_i[i] = (int)d->epi_p[i]; }
+    HB_REQUIRE(!(d->epilogue == HB_EPI_DIVI_CAST && p.epi_i[0] == 0), HB_ERR_INVALID, "hb_local_op: division by zero in epilogue");
+    p.cval_f = (float)d->boundary_const; p.cval_i = (int)d->boundary_const;
+
+    const bool facc = d->acc_dtype == HB_F32;
+    HB_REQUIRE(facc || d->acc_dtype == HB_S32 || d->acc_dtype == HB_S16, HB_ERR_UNSUPPORTED, "hb_local_op: accumulator type %d unsupported", d->acc_dtype);
+    HB_REQUIRE(!(d->tap == HB_TAP_MUL && !facc && !d->coef_s32), HB_ERR_UNSUPPORTED,
+               "hb_local_op: float mask with an integer accumulator is not supported");
+    const int n = d->size_x * d->size_y;
+    int visited = 0;
+    for (int k = 0; k < n; ++k) {
+        bool on = true;
+        if (d->kind == HB_LOCAL_REDUCE_DOMAIN) {
+            if (d->domain) on = d->domain[k] != 0;
+            else if (d->tap == HB_TAP_MUL) on = d->coef_f32 ? d->coef_f32[k] != 0.0f : d->coef_s32[k] != 0;
+        }
+        if (on) { p.dom[k >> 5] |= 1u << (k & 31); ++visited; }
+        if (d->tap == HB_TAP_MUL) {
+            // holes contribute coef 0 in the SUM fast path (exact: x + 0 == x)
+            if (facc) p.coef.f[k] = on ? (d->coef_f32 ? d->coef_f32[k] : (float)d->coef_s32[k]) : 0.0f;
+            else p.coef.i[k] = on ? d->coef_s32[k] : 0;
+        }
+    }
+    HB_REQUIRE(visited > 0, HB_ERR_INVALID, "hb_local_op: empty domain");
+    const bool fast = d->reduce_mode == HB_REDUCE_SUM && d->tap == HB_TAP_MUL;
+
+    cudaStream_t s = (cudaStream_t)stream;
+    OpScope scope(s, "hb_local_op");
+    int rc = HB_ERR_UNSUPPORTED;
+    const int it = in.dtype, ot = out.dtype;
+    if (facc) {
+        if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, float, uchar>(p, fast, s);
+        else if (it == HB_F32 && ot == HB_F32) rc = launch_local<float, float, float>(p, fast, s);
+        else if (it == HB_S8 && ot == HB_S8) rc = launch_local<signed char, float, signed char>(p, fast, s);
+    } else {
+        if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, int, uchar>(p, fast, s);
+        else if (it == HB_U8 && ot == HB_S32) rc = launch_local<uchar, int, int>(p, fast, s);
+        else if (it == HB_U8 && ot == HB_S16) rc = launch_local<uchar, int, short>(p, fast, s);
+        else if (it == HB_S16 && ot == HB_S16) rc = launch_local<short, int, short>(p, fast, s);
+    }
+    HB_REQUIRE(rc != HB_ERR_UNSUPPORTED, HB_ERR_UNSUPPORTED,
+               "hb_local_op: no device kernel for (in %d, acc %d, out %d); there is no CPU fallback", it, d->acc_dtype, ot);
+    return scope.finish();
+}

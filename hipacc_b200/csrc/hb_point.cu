@@ -1,0 +1,187 @@
+// hb_point.cu -- point operators (pure streaming maps over 1-3 inputs) for sm_100a.
+//
+// Replaces generated point-operator kernels (bodies that only use in() / output(),
+// lib/Analysis/KernelStatistics.cpp:366-388) -- e.g. SobelCombine (Sobel/src/main.cpp:76-98),
+// Square1/Square2/HarrisCorner (Harris_Corner/src/main.cpp:78-164), Subsample /
+// DifferenceOfGaussian / Restore / Blend (Gaussian_Laplacian_Pyramid/src/main.cpp:52-135).
+// Inputs may be interpolating accessors (NN, LF; dsl/image.hpp:390-422) with the DSL's default
+// CLAMP boundary (dsl/image.hpp:616-620).
+//
+// HBM-bound: 4 pixels per thread with vector loads / stores when nothing interpolates and the rows
+// are aligned; a scalar path otherwise.  Integer promotions and the truncating store are part of
+// the result and are kept exactly (C semantics of the sample bodies).
+#include "hb_common.cuh"
+#include "hb_internal.h"
+
+#include <cstring>
+
+namespace hb {
+
+struct PointIn {
+    const void *p;
+    int stride, iw, ih;
+    int w, h, ox, oy;  // accessor region
+    int interp;
+};
+struct PointParams {
+    PointIn in[3];
+    int n_in;
+    void *out;
+    int out_stride, out_ox, out_oy, is_w, is_h;
+    int op;
+    float pf[2];
+    int pi[2];
+};
+
+// accessor value for output pixel (gx,gy) through NN / LF interpolation (dsl/image.hpp:390-422)
+template <typename T>
+__device__ __forceinline__ T fetch_interp(const PointIn &a, int gx, int gy, int is_w, int is_h) {
+    ImgRef<T> im{static_cast<const T *>(a.p), a.stride, a.iw, a.ih};
+    const Window w{a.ox, a.ox + a.w, a.oy, a.oy + a.h, HB_BOUNDARY_CLAMP};
+    if (a.interp == HB_INTERP_NO) return im.p[(size_t)(a.oy + gy) * a.stride + a.ox + gx];
+    const float stride_x = __fdiv_rn((float)a.w, (float)is_w);
+    const float stride_y = __fdiv_rn((float)a.h, (float)is_h);
+    // offset + stride/2 + stride*(x - is_offset)   (left to right, separately rounded)
+    const float x_mapped = __fadd_rn(__fadd_rn((float)a.ox, __fdiv_rn(stride_x, 2.0f)), __fmul_rn(stride_x, (float)gx));
+    const float y_mapped = __fadd_rn(__fadd_rn((float)a.oy, __fdiv_rn(stride_y, 2.0f)), __fmul_rn(stride_y, (float)gy));
+    if (a.interp == HB_INTERP_NN) return fetch_bh(im, w, __float2int_rz(x_mapped), __float2int_rz(y_mapped), T(0));
+    float xb = __fadd_rn(x_mapped, -0.5f), yb = __fadd_rn(y_mapped, -0.5f);
+    if (xb < 0.0f) xb = 0.0f;
+    if (yb < 0.0f) yb = 0.0f;
+    const int x_int = __float2int_rz(xb), y_int = __float2int_rz(yb);
+    const float xf = __fadd_rn(xb, -(float)x_int), yf = __fadd_rn(yb, -(float)y_int);
+    const float omx = __fadd_rn(1.0f, -xf), omy = __fadd_rn(1.0f, -yf);
+    const float p00 = (float)fetch_bh(im, w, x_int, y_int, T(0));
+    const float p10 = (float)fetch_bh(im, w, x_int + 1, y_int, T(0));
+    const float p01 = (float)fetch_bh(im, w, x_int, y_int + 1, T(0));
+    const float p11 = (float)fetch_bh(im, w, x_int + 1, y_int + 1, T(0));
+    float r = __fmul_rn(__fmul_rn(omx, omy), p00);
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(xf, omy), p10));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(omx, yf), p01));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(xf, yf), p11));
+    return cast_out<T, float>(r);  // convert<T>(float) = C cast (dsl/types.hpp:115-117)
+}
+
+template <typename TI, typename TO>
+__device__ __forceinline__ TO point_eval(int op, TI a, TI b, TI c, const PointParams &p) {
+    constexpr bool isf = DtypeOf<TI>::v == HB_F32;
+    switch (op) {
+    case HB_POINT_COPY: return (TO)a;
+    case HB_POINT_SQUARE: return isf ? (TO)__fmul_rn((float)a, (float)a) : (TO)((int)a * (int)a);
+    case HB_POINT_MUL: return isf ? (TO)__fmul_rn((float)a, (float)b) : (TO)((int)a * (int)b);
+    case HB_POINT_SUB: return isf ? (TO)__fadd_rn((float)a, -(float)b) : (TO)((int)a - (int)b);
+    case HB_POINT_ADD: return isf ? (TO)__fadd_rn((float)a, (float)b) : (TO)((int)a + (int)b);
+    case HB_POINT_BLEND: return isf ? (TO)__fadd_rn((float)a, __fdiv_rn((float)b, 2.0f)) : (TO)((int)a + (int)b / 2);
+    case HB_POINT_SOBEL_COMBINE: {
+        const int norm = p.pi[0];
+        const TI in1 = (TI)((int)a / norm), in2 = (TI)((int)b / norm);
+        float r = __fsqrt_rn((float)((int)in1 * (int)in1 + (int)in2 * (int)in2));
+        r = r < 255.0f ? r : 255.0f;
+        r = r > 0.0f ? r : 0.0f;
+        return cast_out<TO, float>(r);
+    }
+    case HB_POINT_HARRIS: {
+        // R = ((x*y) - (xy*xy)) - (k*(x+y)*(x+y)): int determinant converted to float, float trace term,
+        // no FMA contraction (it can flip the threshold test)
+        const int x = (int)a, y = (int)b, xy = (int)c;
+        const float det = (float)(x * y - xy * xy);
+        const float s = (float)(x + y);
+        const float tr = __fmul_rn(__fmul_rn(p.pf[0], s), s);
+        const float R = __fadd_rn(det, -tr);
+        return (TO)(R > p.pf[1] ? 1 : 0);
+    }
+    default: return (TO)0;
+    }
+}
+
+template <typename TI, typename TO, bool VEC>
+__global__ void __launch_bounds__(256) point_kernel(const __grid_constant__ PointParams p) {
+    const int vw = (p.is_w + 3) / 4;  // 4-pixel groups per row
+    const long long total = (long long)vw * p.is_h;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int gy = (int)(g / vw), gx = (int)(g - (long long)gy * vw) * 4;
+        TI v[3][4];
+        if (VEC && gx + 3 < p.is_w) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < p.n_in) load4(static_cast<const TI *>(p.in[k].p) + (size_t)(p.in[k].oy + gy) * p.in[k].stride + p.in[k].ox + gx, v[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < p.n_in)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[k][i] = gx + i < p.is_w ? fetch_interp<TI>(p.in[k], gx + i, gy, p.is_w, p.is_h) : TI(0);
+        }
+        TO o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = point_eval<TI, TO>(p.op, v[0][i], p.n_in > 1 ? v[1][i] : TI(0), p.n_in > 2 ? v[2][i] : TI(0), p);
+        TO *dst = static_cast<TO *>(p.out) + (size_t)(p.out_oy + gy) * p.out_stride + p.out_ox + gx;
+        if (VEC && gx + 3 < p.is_w) {
+            store4(dst, o);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (gx + i < p.is_w) dst[i] = o[i];
+        }
+    }
+}
+
+template <typename TI, typename TO>
+static int launch_point(const PointParams &p, bool vec, cudaStream_t s) {
+    const long long total = (long long)((p.is_w + 3) / 4) * p.is_h;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 32;  // grid-stride beyond a few waves
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (vec) point_kernel<TI, TO, true><<<(unsigned)blocks, 256, 0, s>>>(p);
+    else point_kernel<TI, TO, false><<<(unsigned)blocks, 256, 0, s>>>(p);
+    g_launches++;
+    return HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_point_op(const hb_point_desc *d, void *stream) {
+    HB_REQUIRE(d && d->n_in >= 1 && d->n_in <= 3, HB_ERR_INVALID, "hb_point_op: bad descriptor");
+    hb_view out = norm_view(d->out);
+    HB_REQUIRE(view_ok(out), HB_ERR_INVALID, "hb_point_op: malformed output view");
+    PointParams p;
+    memset(&p, 0, sizeof(p));
+    const int it = d->in[0].dtype;
+    const size_t ies = dtype_size(it), oes = dtype_size(out.dtype);
+    bool vec = (out.stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out.data) + (size_t)out.offset_x * oes) % (4 * oes) == 0);
+    for (int k = 0; k < d->n_in; ++k) {
+        hb_view v = norm_view(d->in[k]);
+        HB_REQUIRE(view_ok(v) && v.dtype == it, HB_ERR_INVALID, "hb_point_op: malformed input view %d (all inputs share one pixel type)", k);
+        const int ip = d->interp[k];
+        HB_REQUIRE(ip >= HB_INTERP_NO && ip <= HB_INTERP_LF, HB_ERR_UNSUPPORTED, "hb_point_op: interpolation mode %d not implemented", ip);
+        HB_REQUIRE(ip != HB_INTERP_NO || (v.width >= out.width && v.height >= out.height), HB_ERR_INVALID,
+                   "hb_point_op: input %d region smaller than the iteration space", k);
+        p.in[k] = PointIn{v.data, v.stride, v.img_width, v.img_height, v.width, v.height, v.offset_x, v.offset_y, ip};
+        vec = vec && ip == HB_INTERP_NO && (v.stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(v.data) + (size_t)v.offset_x * ies) % (4 * ies) == 0);
+    }
+    p.n_in = d->n_in;
+    p.out = out.data; p.out_stride = out.stride; p.out_ox = out.offset_x; p.out_oy = out.offset_y; p.is_w = out.width; p.is_h = out.height;
+    p.op = d->op;
+    for (int i = 0; i < 2; ++i) { p.pf[i] = (float)d->p[i]; p.pi[i] = (int)d->p[i]; }
+    HB_REQUIRE(d->op >= HB_POINT_COPY && d->op <= HB_POINT_HARRIS, HB_ERR_INVALID, "hb_point_op: unknown op %d", d->op);
+    HB_REQUIRE(!(d->op == HB_POINT_SOBEL_COMBINE && p.pi[0] == 0), HB_ERR_INVALID, "hb_point_op: norm == 0");
+    const int need = (d->op == HB_POINT_HARRIS) ? 3 : (d->op == HB_POINT_COPY || d->op == HB_POINT_SQUARE) ? 1 : 2;
+    HB_REQUIRE(d->n_in == need, HB_ERR_INVALID, "hb_point_op: op %d takes %d inputs", d->op, need);
+
+    cudaStream_t s = (cudaStream_t)stream;
+    OpScope scope(s, "hb_point_op");
+    int rc = HB_ERR_UNSUPPORTED;
+    const int ot = out.dtype;
+    if (it == HB_F32 && ot == HB_F32) rc = launch_point<float, float>(p, vec, s);
+    else if (it == HB_S16 && ot == HB_S16) rc = launch_point<short, short>(p, vec, s);
+    else if (it == HB_S16 && ot == HB_U8) rc = launch_point<short, uchar>(p, vec, s);
+    else if (it == HB_S32 && ot == HB_U8) rc = launch_point<int, uchar>(p, vec, s);
+    else if (it == HB_S32 && ot == HB_S32) rc = launch_point<int, int>(p, vec, s);
+    else if (it == HB_U8 && ot == HB_U8) rc = launch_point<uchar, uchar>(p, vec, s);
+    else if (it == HB_S8 && ot == HB_S8) rc = launch_point<signed char, signed char>(p, vec, s);
+    HB_REQUIRE(rc == HB_OK, HB_ERR_UNSUPPORTED, "hb_point_op: no device kernel for (in %d, out %d); no CPU fallback", it, ot);
+    return scope.finish();
+}

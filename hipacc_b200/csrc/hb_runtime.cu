@@ -1,0 +1,174 @@
+// hb_runtime.cu -- device / runtime layer of the C ABI: init, image memory, copies, timing, logging.
+// Replaces runtime/hipacc_cu_standalone.hpp:113-216,277-329 and runtime/hipacc_cu.tpp:43-193
+// (paths relative to the Hipacc tree).  No textures, no NVRTC, no OpenCL, no CPU fallback.
+#include "hb_internal.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace hb {
+
+std::atomic<long long> g_launches{0};
+bool g_timing = false;
+static hb_log_fn g_log = nullptr;
+static thread_local std::string g_last_error;
+static thread_local float g_last_ms = 0.0f;  // thread_local like HipaccKernelTimingBase (hipacc_base_standalone.hpp:35-39)
+static int g_device = -1;
+static int g_sms = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
+void set_last_error(const std::string &s) { g_last_error = s; }
+
+void log_msg(int level, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (level >= 2) g_last_error = buf;
+    if (g_log) g_log(level, buf);
+    else fprintf(level == 0 ? stdout : stderr, "<HIPACC-B200:> %s\n", buf);
+}
+
+int sm_count() {
+    if (g_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_sms <= 0) g_sms = 148;
+    }
+    return g_sms;
+}
+
+OpScope::OpScope(cudaStream_t s, const char *n) : stream(s), name(n) {
+    if (g_timing) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        cudaEventRecord(g_ev0, stream);
+    }
+}
+int OpScope::finish() {
+    int rc = check_cuda(cudaGetLastError(), name);
+    if (g_timing) {
+        cudaEventRecord(g_ev1, stream);
+        rc |= check_cuda(cudaEventSynchronize(g_ev1), name);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+        g_last_ms = ms;
+    }
+    return rc ? HB_ERR_CUDA : HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hb_init(int device) {
+    int n = hb_device_count();
+    HB_REQUIRE(n > 0, HB_ERR_NO_DEVICE, "hb_init: no CUDA device visible (this library has no CPU fallback)");
+    HB_REQUIRE(device >= 0 && device < n, HB_ERR_INVALID, "hb_init: device %d out of range (0..%d)", device, n - 1);
+    int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice()");
+    if (rc) return rc;
+    cudaDeviceProp p;
+    rc = check_cuda(cudaGetDeviceProperties(&p, device), "cudaGetDeviceProperties()");
+    if (rc) return rc;
+    g_device = device;
+    g_sms = p.multiProcessorCount;
+    HB_REQUIRE(p.major >= 10, HB_ERR_UNSUPPORTED, "hb_init: device %d (%s, sm_%d%d) is not a Blackwell part; kernels are built for sm_100a only",
+               device, p.name, p.major, p.minor);
+    return HB_OK;
+}
+
+int hb_sm_count(void) { return sm_count(); }
+void hb_set_log_callback(hb_log_fn fn) { g_log = fn; }
+const char *hb_last_error(void) { return g_last_error.c_str(); }
+void hb_set_timing(int enabled) { g_timing = enabled != 0; }
+float hb_last_kernel_ms(void) { return g_last_ms; }
+long long hb_launch_count(void) { return g_launches.load(); }
+int hb_stream_synchronize(void *stream) { return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize()"); }
+
+int hb_image_create(int dtype, int width, int height, int alignment, hb_view *out) {
+    HB_REQUIRE(out && width > 0 && height > 0 && dtype >= HB_U8 && dtype <= HB_F32, HB_ERR_INVALID, "hb_image_create: bad arguments");
+    const int es = dtype_size(dtype);
+    if (alignment <= 0) alignment = 256;
+    // alignment has to be a multiple of sizeof(T) (runtime/hipacc_cu.tpp:54-57)
+    alignment = ((alignment + es - 1) / es) * es;
+    const size_t per = (size_t)alignment / es;
+    const size_t stride = (((size_t)width + per - 1) / per) * per;
+    void *p = nullptr;
+    int rc = check_cuda(cudaMalloc(&p, stride * (size_t)height * es), "cudaMalloc()");
+    if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->data = p; out->dtype = dtype; out->img_width = width; out->img_height = height; out->stride = (int)stride;
+    out->width = width; out->height = height;
+    return HB_OK;
+}
+
+int hb_image_destroy(hb_view *img) {
+    if (!img || !img->data) return HB_OK;
+    int rc = check_cuda(cudaFree(img->data), "cudaFree()");
+    img->data = nullptr;
+    return rc;
+}
+
+int hb_image_wrap(void *device_ptr, int dtype, int width, int height, int stride, hb_view *out) {
+    HB_REQUIRE(out && device_ptr && width > 0 && height > 0 && stride >= width, HB_ERR_INVALID, "hb_image_wrap: bad arguments");
+    memset(out, 0, sizeof(*out));
+    out->data = device_ptr; out->dtype = dtype; out->img_width = width; out->img_height = height; out->stride = stride;
+    out->width = width; out->height = height;
+    return HB_OK;
+}
+
+int hb_image_write(const hb_view *img, const void *host, void *stream) {
+    HB_REQUIRE(img && img->data && host, HB_ERR_INVALID, "hb_image_write: bad arguments");
+    const size_t es = dtype_size(img->dtype);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemcpy2DAsync(img->data, (size_t)img->stride * es, host, (size_t)img->img_width * es,
+                                          (size_t)img->img_width * es, img->img_height, cudaMemcpyHostToDevice, s),
+                        "cudaMemcpy2DAsync(H2D)");
+    if (rc) return rc;
+    return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize()");  // blocking like the reference
+}
+
+int hb_image_read(const hb_view *img, void *host, void *stream) {
+    HB_REQUIRE(img && img->data && host, HB_ERR_INVALID, "hb_image_read: bad arguments");
+    const size_t es = dtype_size(img->dtype);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = check_cuda(cudaMemcpy2DAsync(host, (size_t)img->img_width * es, img->data, (size_t)img->stride * es,
+                                          (size_t)img->img_width * es, img->img_height, cudaMemcpyDeviceToHost, s),
+                        "cudaMemcpy2DAsync(D2H)");
+    if (rc) return rc;
+    return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize()");
+}
+
+int hb_image_copy(const hb_view *src, const hb_view *dst, void *stream) {
+    HB_REQUIRE(src && dst && src->data && dst->data, HB_ERR_INVALID, "hb_image_copy: bad arguments");
+    HB_REQUIRE(src->img_width == dst->img_width && src->img_height == dst->img_height && src->dtype == dst->dtype, HB_ERR_INVALID,
+               "hb_image_copy: extents / types differ");
+    const size_t es = dtype_size(src->dtype);
+    return check_cuda(cudaMemcpy2DAsync(dst->data, (size_t)dst->stride * es, src->data, (size_t)src->stride * es,
+                                        (size_t)src->img_width * es, src->img_height, cudaMemcpyDeviceToDevice, (cudaStream_t)stream),
+                      "cudaMemcpy2DAsync(D2D)");
+}
+
+int hb_image_copy_region(const hb_view *src_, const hb_view *dst_, void *stream) {
+    HB_REQUIRE(src_ && dst_ && src_->data && dst_->data, HB_ERR_INVALID, "hb_image_copy_region: bad arguments");
+    hb_view src = norm_view(*src_), dst = norm_view(*dst_);
+    HB_REQUIRE(src.dtype == dst.dtype && view_ok(src) && view_ok(dst), HB_ERR_INVALID, "hb_image_copy_region: bad views");
+    HB_REQUIRE(src.width <= dst.img_width - dst.offset_x && src.height <= dst.img_height - dst.offset_y, HB_ERR_INVALID,
+               "hb_image_copy_region: source region does not fit at the destination offset");
+    const size_t es = dtype_size(src.dtype);
+    char *d = (char *)dst.data + ((size_t)dst.offset_y * dst.stride + dst.offset_x) * es;
+    const char *s = (const char *)src.data + ((size_t)src.offset_y * src.stride + src.offset_x) * es;
+    return check_cuda(cudaMemcpy2DAsync(d, (size_t)dst.stride * es, s, (size_t)src.stride * es, (size_t)src.width * es, src.height,
+                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream),
+                      "cudaMemcpy2DAsync(D2D region)");
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads without a GPU and exports every symbol
+include/hipacc_b200.h declares; host-side logic (views, specs, pyramid sizes).  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hipacc_b200 import _abi as A, specs as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_and_export_list_agree():
+    hdr = open(os.path.join(ROOT, "include", "hipacc_b200.h")).read()
+    declared = set(re.findall(r"\b(hb_[a-z0-9_]+)\s*\(", hdr)) - {"hb_log_fn"}
+    assert declared == set(A.EXPORTS), declared ^ set(A.EXPORTS)
+
+
+def test_library_loads_and_exports_all_symbols(hb):
+    L = hb.lib()
+    for sym in A.EXPORTS:
+        assert hasattr(L, sym), f"libhipacc_b200.so does not export {sym}"
+
+
+def test_no_device_is_an_error_not_a_fallback(hb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    L = hb.lib()
+    assert L.hb_device_count() == 0
+    assert L.hb_init(0) == A.HB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in L.hb_last_error()
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed by hand from include/hipacc_b200.h on LP64
+    assert C.sizeof(A.hb_view) == 48
+    assert C.sizeof(A.hb_local_desc) == 2 * 48 + 6 * 4 + 3 * 8 + 4 + 4 + 8 + 4 + 4 + 24
+    assert C.sizeof(A.hb_point_desc) == 3 * 48 + 12 + 4 + 48 + 4 + 4 + 16
+    assert C.sizeof(A.hb_harris_desc) == 2 * 48 + 8
+    assert C.sizeof(A.hb_pyr_up_desc) == 4 * 48
+
+
+def test_struct_layouts_match_the_compiler(tmp_path):
+    """Compile a tiny C program against the real header and compare sizeof / offsetof."""
+    import subprocess
+    src = tmp_path / "lay.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hipacc_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hb_view), sizeof(hb_local_desc),'
+                   'sizeof(hb_bilateral_desc), sizeof(hb_point_desc), sizeof(hb_harris_desc), sizeof(hb_pyr_down_desc),'
+                   'sizeof(hb_pyr_up_desc), offsetof(hb_local_desc, epi_p), offsetof(hb_point_desc, p));return 0;}\n')
+    exe = tmp_path / "lay"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(A.hb_view), C.sizeof(A.hb_local_desc), C.sizeof(A.hb_bilateral_desc), C.sizeof(A.hb_point_desc),
+            C.sizeof(A.hb_harris_desc), C.sizeof(A.hb_pyr_down_desc), C.sizeof(A.hb_pyr_up_desc),
+            A.hb_local_desc.epi_p.offset, A.hb_point_desc.p.offset]
+    assert got == want
+
+
+def test_pyramid_sizes_truncate_like_the_reference():
+    assert S.pyramid_sizes(16384, 16384, 8)[-1] == (128, 128)
+    assert S.pyramid_sizes(101, 67, 3) == [(101, 67), (50, 33), (25, 16)]
+    with pytest.raises(AssertionError):
+        S.pyramid_sizes(8, 8, 5)
+
+
+def test_spec_fill_keeps_host_arrays_alive():
+    spec = S.gaussian_blur(np.ones((3, 3), np.float32) / 9)
+    d = A.hb_local_desc()
+    spec.fill(d)
+    assert d.size_x == 3 and d.epilogue == A.EPI_ADD_CAST and d.epi_p[0] == 0.5
+    assert abs(d.coef_f32[4] - 1 / 9) < 1e-7 and not d.coef_s32
