@@ -1,0 +1,85 @@
+"""CPU tests of the multi-GPU host logic (world_size 2 and 3, gloo): strip partition + halo exchange
+reproduce the boundary-extended global image, and the oracle applied per strip with ghost rows equals
+the oracle on the whole image (the property the sharded CUDA path relies on)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hipacc_b200 import _abi as A, masks as M, specs as S, strips, synth
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, boundary, radius, H, W, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = strips.StripPlan(W, H, world, rank, radius, boundary)
+        plan.validate()
+        stride = W + 5  # padded rows: whole-row messages include the padding
+        buf = torch.full((plan.buffer_rows, stride), -1.0, dtype=torch.float32)
+        strips.owned(buf, plan)[:, :W] = torch.from_numpy(synth.image_np("float32", W, plan.rows, seed=3, y0=plan.y0))
+        strips.exchange_halos(buf, plan)
+        mn, mx, sm = strips.allreduce_minmaxsum(float(strips.owned(buf, plan)[:, :W].min()), float(strips.owned(buf, plan)[:, :W].max()),
+                                                float(strips.owned(buf, plan)[:, :W].double().sum()))
+        q.put((rank, plan.y0, plan.y1, plan.ghost_top, plan.ghost_bottom, buf[:, :W].numpy().copy(), (mn, mx, sm)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, boundary, radius, H=37, W=19):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, boundary, radius, H, W, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("boundary", [A.MIRROR, A.CLAMP, A.REPEAT])
+def test_halo_exchange_and_strip_parity(oracle, world, boundary):
+    H, W, R = 37, 19, 2
+    full = synth.image_np("float32", W, H, seed=3)
+    res = _run(world, boundary, R, H, W)
+    spec = S.domain_reduce_f32(M.LAPLACE5.astype(np.float32), boundary)
+    want = oracle.local_op(spec, full)
+    rows = 0
+    for rank, y0, y1, gt, gb, buf, red in res:
+        # ghost rows hold the neighbours' real rows (cyclic neighbours for REPEAT)
+        ext = np.concatenate([full[(np.arange(y0 - gt, y0)) % H], full[y0:y1], full[(np.arange(y1, y1 + gb)) % H]])
+        np.testing.assert_array_equal(buf, ext)
+        roi = (W, y1 - y0, 0, gt)
+        got = oracle.local_op(spec, np.ascontiguousarray(buf), roi_in=roi, roi_out=roi, ghost=(gt, gb))
+        np.testing.assert_array_equal(got[gt:gt + y1 - y0], want[y0:y1])   # strip result == rows of the global result
+        rows += y1 - y0
+        assert np.float32(red[0]) == full.min() and np.float32(red[1]) == full.max()
+        assert abs(red[2] - full.astype(np.float64).sum()) < 1e-9 * full.sum()
+    assert rows == H
+
+
+def test_plan_partitions_every_row_once():
+    for H, world in [(37, 3), (8192, 8), (4097, 4), (5, 5)]:
+        plans = [strips.StripPlan(16, H, world, r, 1) for r in range(world)]
+        assert plans[0].y0 == 0 and plans[-1].y1 == H
+        assert all(plans[i].y1 == plans[i + 1].y0 for i in range(world - 1))
+        assert plans[0].ghost_top == 0 and plans[-1].ghost_bottom == 0
+    with pytest.raises(AssertionError):
+        strips.StripPlan(16, 8, 8, 0, 2).validate()
