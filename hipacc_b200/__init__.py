@@ -188,13 +188,14 @@ def reduce(src, mode, roi=None, stream=None):
     return res[0]
 
 
-def harris(src, k=masks.HARRIS_K, threshold=masks.HARRIS_THRESHOLD, dst=None, stream=None):
-    """Fused Harris corner detector (uchar -> uchar), one kernel (hb_harris)."""
+def harris(src, k=masks.HARRIS_K, threshold=masks.HARRIS_THRESHOLD, dst=None, roi=None, ghost=(0, 0), stream=None):
+    """Fused Harris corner detector (uchar -> uchar), one kernel (hb_harris).  `roi` / `ghost` select the
+    owned rows of a strip buffer whose ghost rows hold real neighbour data (row-strip sharding)."""
     import torch
     if dst is None:
         dst = torch.zeros_like(src)
     d = A.hb_harris_desc()
-    d.in_, d.out = view(src), view(dst)
+    d.in_, d.out = view(src, roi, ghost), view(dst, roi)
     d.k, d.threshold = float(k), float(threshold)
     _check(lib().hb_harris(C.byref(d), stream_ptr(stream)), "hb_harris")
     return dst

@@ -52,8 +52,10 @@ __global__ void __launch_bounds__(HBX *HBY) harris_fused_kernel(const __grid_con
     for (int q = tid; q < HMID_ROWS * (HTW + 2); q += HBX * HBY) {
         const int jy = q / (HTW + 2) - 1, jx = q - (jy + 1) * (HTW + 2) - 1;
         int cx = gx0 + jx, cy = gy0 + jy;
+        // the intermediates live on the same extent as the input window: [0, w) horizontally and, with ghost
+        // rows (row-strip sharding), [-ghost_top, h + ghost_bottom) vertically -- CLAMP only at the global edge
         cx = min(max(cx, 0), p.w - 1) - gx0;  // tile-local clamped position
-        cy = min(max(cy, 0), p.h - 1) - gy0;
+        cy = min(max(cy, p.win.lo_y - p.in_oy), p.win.hi_y - 1 - p.in_oy) - gy0;
         const int *c = tin + (cy + 2) * HIN_COLS + (cx + 4);
         const int a00 = c[-HIN_COLS - 1], a01 = c[-HIN_COLS], a02 = c[-HIN_COLS + 1];
         const int a10 = c[-1], a12 = c[1];
@@ -150,8 +152,6 @@ extern "C" int hb_harris(const hb_harris_desc *d, void *stream) {
     p.in_ox = in.offset_x; p.in_oy = in.offset_y;
     p.out_stride = out.stride; p.out_ox = out.offset_x; p.out_oy = out.offset_y; p.w = out.width; p.h = out.height;
     p.k = d->k; p.threshold = d->threshold;
-    HB_REQUIRE(in.ghost_top == 0 && in.ghost_bottom == 0, HB_ERR_UNSUPPORTED,
-               "hb_harris: ghost rows are handled by the strip runner through offset views (not implemented in the fused kernel)");
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_harris");
     dim3 grid((p.w + HTW - 1) / HTW, (p.h + HTH - 1) / HTH);

@@ -5,7 +5,7 @@
 // HOST pointers in hb_view::data.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs may load this library; the product never does.
 //
-// Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function here
+// Parity status: PINNED.  tests/test_oracle.py checks every function here
 // bit-for-bit (uchar/int) or to 1 ulp-level tolerance (float) against oracle/_ref
 // (the reference's own DSL headers + sample kernels executed as C++), against the samples'
 // embedded plain-C checkers, against SURVEY.md appendix A known-answer vectors and against

@@ -303,6 +303,23 @@ def test_harris_noise_image(hb, oracle, dev):
     np.testing.assert_array_equal(to_np(hb.harris(to_dev(hb, img, dev))), oracle.harris(img))
 
 
+@pytest.mark.parametrize("R", [2, 3])
+def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
+    """C4 sharding: each strip + R >= 2 ghost rows of real neighbour data gives exactly its rows of the full result
+    (the 5x5 receptive field of the fused pipeline; CLAMP of image AND intermediates only at the global edge)."""
+    H, W = 230, 300
+    img = synth.image_np("uint8", W, H, seed=8)
+    full = oracle.harris(img)
+    for n in (2, 3, 5):
+        for r in range(n):
+            y0, y1 = H * r // n, H * (r + 1) // n
+            g0, g1 = min(R, y0), min(R, H - y1)
+            strip = np.ascontiguousarray(img[y0 - g0:y1 + g1])
+            roi = (W, y1 - y0, 0, g0)
+            out = hb.harris(to_dev(hb, strip, dev), roi=roi, ghost=(g0, g1))
+            np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
+
+
 # ------------------------------------------------------------------ pyramid
 @pytest.mark.parametrize("idx", range(len(cases.PYR_CASES)))
 @pytest.mark.parametrize("with_tmp", [False, True], ids=["fused_down", "unfused_down"])
