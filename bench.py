@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--extra", action="store_true", help="also time the other BASELINE configs (C1, C3, C4 strip, C5) into 'operators'")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning sweeps only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -230,12 +231,12 @@ def main():
     px_per_step = len(OPS) * W * plan.rows * world      # whole job
     value = px_per_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (local_tiled_kernel<float,float,float,3,3,0>): per-launch average
+    # ---- roofline of the dominant kernel (local_tma_f32_kernel<3,3,...>, hb_local_tma.cu): per-launch average
     per_launch_ms = ms / (steps * len(OPS))
     peak, peak_src = peaks()
     achieved = ALG_BYTES_PER_PX * W * plan.rows / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "local_tiled_kernel<float,float,float,3,3,0>", "peak_source": peak_src,
+                "traffic": None, "kernel": "local_tma_f32_kernel<3,3,Mask*> (TMA-pipelined, persistent)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_PX * W * plan.rows, "avg_launch_ms": per_launch_ms}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
@@ -259,7 +260,7 @@ def main():
         step()
         for v, h in zip(own_out, h_out):
             L.hb_image_read(C.byref(v), C.c_void_p(h.data_ptr()), sp)            # HBM -> host (blocking, like hipaccReadMemory)
-    e2e_steps = max(2, min(steps, 5))
+    e2e_steps = 0 if args.no_e2e else max(2, min(steps, 5))
     e2e_step()
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -268,7 +269,7 @@ def main():
         e2e_step()
     e3.record(stream)
     sync_all()
-    e2e_s = e2.elapsed_time(e3) * 1e-3 / e2e_steps
+    e2e_s = e2.elapsed_time(e3) * 1e-3 / max(e2e_steps, 1)
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)

@@ -19,7 +19,7 @@ LIB = os.path.join(OUT_DIR, "libhipacc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-std=c++17", "-O3", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC",
-          "-ccbin", "/usr/bin/g++"]
+          "-ccbin", "/usr/bin/g++"] + os.environ.get("HB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources():

@@ -15,97 +15,11 @@
 //     row-major order, so results are bit-identical to the DSL's sequential fold.
 //   * mask coefficients live in the kernel parameter (constant) bank and the tap loops are fully
 //     unrolled for 3x3 / 5x5 / 7x7; other sizes use the generic kernel below.
-#include "hb_common.cuh"
-#include "hb_internal.h"
+#include "hb_local.cuh"
 
 #include <cstring>
 
 namespace hb {
-
-constexpr int kMaxTaps = 169;  // up to 13 x 13
-
-struct LocalParams {
-    const void *in;
-    void *out;
-    int in_stride, in_iw, in_ih;
-    Window win;
-    int in_ox, in_oy;  // IS-relative (0,0) reads input pixel (in_ox, in_oy)  (dsl/image.hpp:412)
-    int out_stride, out_ox, out_oy, is_w, is_h;
-    int size_x, size_y;
-    int reduce_mode, tap, acc_s16, epilogue;
-    float epi_f[3];
-    int epi_i[3];
-    float cval_f;
-    int cval_i;
-    unsigned dom[6];  // bit k: tap k (row-major) is visited
-    union {
-        float f[kMaxTaps];
-        int i[kMaxTaps];
-    } coef;
-};
-
-// ---- arithmetic in the accumulation type (float: separately rounded mul / add) ----
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ int mul_rn(int a, int b) { return a * b; }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ int add_rn(int a, int b) { return a + b; }
-
-template <typename TS> __device__ __forceinline__ TS fold_identity(int mode);
-template <> __device__ __forceinline__ float fold_identity<float>(int mode) {
-    return mode == HB_REDUCE_SUM ? 0.0f : mode == HB_REDUCE_PROD ? 1.0f : mode == HB_REDUCE_MIN ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
-}
-template <> __device__ __forceinline__ int fold_identity<int>(int mode) {
-    return mode == HB_REDUCE_SUM ? 0 : mode == HB_REDUCE_PROD ? 1 : mode == HB_REDUCE_MIN ? 2147483647 : (-2147483647 - 1);
-}
-template <typename TS>
-__device__ __forceinline__ TS fold(TS acc, TS v, int mode) {
-    switch (mode) {
-    case HB_REDUCE_SUM: return add_rn(acc, v);
-    case HB_REDUCE_MIN: return v < acc ? v : acc;  // hipacc::math::min(fun(), result), dsl/kernel.hpp:256
-    case HB_REDUCE_MAX: return v > acc ? v : acc;
-    default: return mul_rn(acc, v);
-    }
-}
-
-template <typename TS> __device__ __forceinline__ TS coef_of(const LocalParams &p, int k);
-template <> __device__ __forceinline__ float coef_of<float>(const LocalParams &p, int k) { return p.coef.f[k]; }
-template <> __device__ __forceinline__ int coef_of<int>(const LocalParams &p, int k) { return p.coef.i[k]; }
-
-template <typename TO>
-__device__ __forceinline__ TO epilogue(float acc, const LocalParams &p) {
-    switch (p.epilogue) {
-    case HB_EPI_ADD_CAST: return cast_out<TO, float>(__fadd_rn(acc, p.epi_f[0]));
-    case HB_EPI_ADD_CLAMP_CAST: {
-        float v = __fadd_rn(acc, p.epi_f[0]);
-        v = v < p.epi_f[2] ? v : p.epi_f[2];
-        v = v > p.epi_f[1] ? v : p.epi_f[1];
-        return cast_out<TO, float>(v);
-    }
-    case HB_EPI_DIVI_CAST: return cast_out<TO, int>(__float2int_rz(acc) / p.epi_i[0]);
-    case HB_EPI_DIVF_CAST: return cast_out<TO, float>(__fdiv_rn(acc, p.epi_f[0]));
-    default: return cast_out<TO, float>(acc);
-    }
-}
-template <typename TO>
-__device__ __forceinline__ TO epilogue(int acc, const LocalParams &p) {
-    if (p.acc_s16) acc = (int)(short)acc;
-    switch (p.epilogue) {
-    case HB_EPI_ADD_CAST: return cast_out<TO, int>(acc + p.epi_i[0]);
-    case HB_EPI_ADD_CLAMP_CAST: {
-        int v = acc + p.epi_i[0];
-        v = min(v, p.epi_i[2]);
-        v = max(v, p.epi_i[1]);
-        return cast_out<TO, int>(v);
-    }
-    case HB_EPI_DIVI_CAST: return cast_out<TO, int>(acc / p.epi_i[0]);
-    case HB_EPI_DIVF_CAST: return cast_out<TO, float>(__fdiv_rn((float)acc, p.epi_f[0]));
-    default: return cast_out<TO, int>(acc);
-    }
-}
-
-template <typename TS> __device__ __forceinline__ TS cval_of(const LocalParams &p);
-template <> __device__ __forceinline__ float cval_of<float>(const LocalParams &p) { return p.cval_f; }
-template <> __device__ __forceinline__ int cval_of<int>(const LocalParams &p) { return p.cval_i; }
 
 // ------------------------------------------------------------------------------------------------
 // Tiled kernel: SX x SY compile-time.  VAR 0: SUM of coef*in (no domain test, hot path).
@@ -306,7 +220,11 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     const int it = in.dtype, ot = out.dtype;
     if (facc) {
         if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, float, uchar>(p, fast, s);
-        else if (it == HB_F32 && ot == HB_F32) rc = launch_local<float, float, float>(p, fast, s);
+        else if (it == HB_F32 && ot == HB_F32) {
+            // hot path: persistent TMA-pipelined kernel (hb_local_tma.cu); anything it does not take runs staged
+            if (fast && d->epilogue == HB_EPI_CAST) rc = launch_local_tma_f32(p, visited == n, s);
+            if (rc == HB_ERR_UNSUPPORTED) rc = launch_local<float, float, float>(p, fast, s);
+        }
         else if (it == HB_S8 && ot == HB_S8) rc = launch_local<signed char, float, signed char>(p, fast, s);
     } else {
         if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, int, uchar>(p, fast, s);

@@ -2,7 +2,9 @@
 // Replaces runtime/hipacc_cu_standalone.hpp:113-216,277-329 and runtime/hipacc_cu.tpp:43-193
 // (paths relative to the Hipacc tree).  No textures, no NVRTC, no OpenCL, no CPU fallback.
 #include "hb_internal.h"
+#include "hb_tma.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -55,6 +57,68 @@ int OpScope::finish() {
         g_last_ms = ms;
     }
     return rc ? HB_ERR_CUDA : HB_OK;
+}
+
+// ---- TMA tensor maps (hb_tma.cuh).  cuTensorMapEncodeTiled is resolved through cudart so the
+// library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else {
+            cudaGetLastError();
+            log_msg(1, "WARNING: cuTensorMapEncodeTiled unavailable; local operators use the all-threads tile loader");
+        }
+    }
+    return fn;
+}
+
+bool tma_addressable(const void *base, int dtype, int stride_px) {
+    const size_t es = dtype_size(dtype);
+    return (reinterpret_cast<uintptr_t>(base) % 16 == 0) && (((size_t)stride_px * es) % 16 == 0);
+}
+
+bool make_tile_map(CUtensorMap *out, const void *base, int dtype, int img_w, int img_h, int stride_px, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !tma_addressable(base, dtype, stride_px)) return false;
+    const size_t es = dtype_size(dtype);
+    if (((size_t)box_w * es) % 16 != 0 || box_w > 256 || box_h > 256 || box_w <= 0 || box_h <= 0) return false;
+    CUtensorMapDataType dt;
+    switch (dtype) {
+    case HB_U8: case HB_S8: dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
+    case HB_U16: case HB_S16: dt = CU_TENSOR_MAP_DATA_TYPE_UINT16; break;
+    case HB_S32: dt = CU_TENSOR_MAP_DATA_TYPE_INT32; break;
+    case HB_U32: dt = CU_TENSOR_MAP_DATA_TYPE_UINT32; break;
+    case HB_F32: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+    default: return false;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)img_w, (cuuint64_t)img_h};
+    const cuuint64_t gstride[1] = {(cuuint64_t)stride_px * es};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    static int promo = -1;  // HB_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B (tuning knob)
+    if (promo < 0) {
+        const char *e = getenv("HB_TMA_L2PROMO");
+        promo = e ? atoi(e) : 2;
+    }
+    const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                    : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    const CUresult r = fn(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        log_msg(1, "WARNING: cuTensorMapEncodeTiled failed (%d) for a %dx%d image, box %dx%d", (int)r, img_w, img_h, box_w, box_h);
+        return false;
+    }
+    return true;
 }
 
 }  // namespace hb

@@ -12,6 +12,6 @@ timeout 600 python bench.py --steps 10 --warmup 3 --extra --no-cpu > $OUT/bench_
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches.csv \
     -k regex:'local_|bilateral_kernel|harris_|pyr_|reduce_|point_kernel' python bench.py --steps 2 --warmup 3 --extra --no-cpu > $OUT/ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'local_tiled_kernel' -s 9 -c 2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'local_tma_f32_kernel|local_tiled_kernel' -s 9 -c 3 \
     -o $OUT/prof_local python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_full.log 2>&1
 ls -la $OUT
