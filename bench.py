@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--extra", action="store_true", help="also time the other BASELINE configs (C1, C3, C4 strip, C5) into 'operators'")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning sweeps only)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every operator from the host instead of replaying a CUDA graph of one step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -194,12 +195,30 @@ def main():
     outs = [hb.empty_image(A.F32, W, plan.buffer_rows, device=dev) for _ in OPS]
     specs = specs_for_workload()
     roi, ghost = plan.roi(), plan.ghost()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)       # the stream every kernel of the timed region runs on
+    torch.cuda.set_stream(stream)
 
-    def step():
+    def step_direct():
         strips.exchange_halos(buf, plan)            # ghost rows from the neighbours (no-op at N = 1)
         for s, o in zip(specs, outs):
             hb.local_op(s, src, dst=o, roi_in=roi, roi_out=roi, ghost=ghost, stream=stream)
+
+    # One step = three operator launches.  At N = 1 the step is captured once into a CUDA graph and replayed
+    # (the reference's own -use-graph mode, runtime/hipacc_cu_standalone.hpp:331-356), so the timed region is
+    # not bounded by the Python host; N > 1 keeps direct launches because the NCCL halo exchange is part of it.
+    use_graph = world == 1 and not args.no_graph
+    launches_per_step = len(OPS)
+    if use_graph:
+        step_direct()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            step_direct()
+
+        def step():
+            graph.replay()
+    else:
+        step = step_direct
 
     def sync_all():
         torch.cuda.synchronize()
@@ -221,7 +240,7 @@ def main():
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = hb.launch_count() - n0
+    launches = launches_per_step * steps if use_graph else hb.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -257,7 +276,7 @@ def main():
 
     def e2e_step():
         L.hb_image_write(C.byref(own_in), C.c_void_p(h_in.data_ptr()), sp)       # host -> HBM (blocking, like hipaccWriteMemory)
-        step()
+        step_direct()
         for v, h in zip(own_out, h_out):
             L.hb_image_read(C.byref(v), C.c_void_p(h.data_ptr()), sp)            # HBM -> host (blocking, like hipaccReadMemory)
     e2e_steps = 0 if args.no_e2e else max(2, min(steps, 5))
@@ -292,7 +311,8 @@ def main():
             "config": {"workload": "C2: Sobel-X + Sobel-Y + Laplace 3x3 local operators, float 8192x8192 per GPU, MIRROR boundary",
                        "pixels_per_step": px_per_step, "operators_per_step": len(OPS), "image": f"{W}x{plan.rows} per rank, {W}x{H * world} global",
                        "l2": "inputs 256 MiB + outputs 768 MiB per step exceed the 126 MB L2; no explicit flush",
-                       "halo_exchange": "none (N=1)" if world == 1 else "1 ghost row per side per step via NCCL send/recv inside the timed region"},
+                       "halo_exchange": "none (N=1)" if world == 1 else "1 ghost row per side per step via NCCL send/recv inside the timed region",
+                       "launch": "CUDA graph replay of the step (3 kernel nodes)" if use_graph else "direct launches through hb_local_op"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if operators:
@@ -343,6 +363,10 @@ def extra_operators(hb, dev, peak):
     part = torch.zeros(4, dtype=torch.float32, device=dev)
     entry("C3_reduce_minmaxsum_f32_8192", 8192 * 8192, 4 * 8192 * 8192, timeit(lambda: hb.reduce_minmaxsum_async(fo, part, stream=stream)),
           "fused min+max+sum, one pass")
+    # 1 read + 1 write references at the same size and timing method: what "HBM roofline" means in this loop
+    c_src, c_dst = f, fo
+    entry("ref_copy_torch_f32_8192", 8192 * 8192, 8 * 8192 * 8192, timeit(lambda: c_dst.copy_(c_src)), "torch copy_ (library kernel), measurement reference only")
+    entry("point_copy_f32_8192", 8192 * 8192, 8 * 8192 * 8192, timeit(lambda: hb.point_op(A.POINT_COPY, [c_src], A.F32, dst=c_dst, stream=stream)), "hb_point_op COPY")
     # C2 single operators
     for nm, m in (("sobel_x", M.SOBEL3_X), ("laplace", M.LAPLACE3)):
         sp = S.domain_reduce_f32(m.astype(np.float32), A.MIRROR)

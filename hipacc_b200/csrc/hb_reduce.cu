@@ -65,32 +65,52 @@ __device__ __forceinline__ MMS block_fold(MMS v) {
     return v;
 }
 
+// Work unit = one "chunk": CHUNK_V consecutive 16-byte vectors of one row (RT threads x UNR independent loads in
+// flight per thread).  Rows are split relative to a 16-byte aligned column; the few scalar pixels before / after
+// the aligned span of a row are folded by the first lanes of the row's first chunk.
+constexpr int UNR = 4;
+constexpr int CHUNK_V = RT * UNR;
+
 __global__ void __launch_bounds__(RT) reduce_mms_f32_kernel(const __grid_constant__ ReduceParams p) {
     const float *in = static_cast<const float *>(p.in);
     const float INF = __int_as_float(0x7f800000);
     float mn = INF, mx = -INF;
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;  // 4 independent float chains per thread
 
-    // rows are split into 4-pixel groups relative to a 16-byte aligned column
     const uintptr_t base_addr = reinterpret_cast<uintptr_t>(in) + (size_t)p.ox * sizeof(float);
     const bool aligned_rows = (p.stride % 4 == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0);
     const int head = aligned_rows ? (int)(((16 - (base_addr & 15)) & 15) / 4) : 0;  // scalar pixels before alignment
     const int head_n = head < p.w ? head : p.w;
     const int nvec = aligned_rows ? (p.w - head_n) / 4 : 0;
     const int tail0 = head_n + nvec * 4;
-    const int units_per_row = nvec + 1;  // unit nvec = scalar head + tail of the row
-    const long long total = (long long)units_per_row * p.h;
-    for (long long u = blockIdx.x * (long long)RT + threadIdx.x; u < total; u += (long long)gridDim.x * RT) {
-        const int y = (int)(u / units_per_row), c = (int)(u - (long long)y * units_per_row);
+    const int cpr = nvec > 0 ? (nvec + CHUNK_V - 1) / CHUNK_V : 1;  // chunks per row
+    const long long total = (long long)cpr * p.h;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int y = (int)(u / cpr), c = (int)(u - (long long)y * cpr);
         const float *row = in + (size_t)(p.oy + y) * p.stride + p.ox;
-        if (c < nvec) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(row + head_n + 4 * c));
-            mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
-            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-            s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
-        } else {
-            for (int x = 0; x < head_n; ++x) { const float e = row[x]; mn = fminf(mn, e); mx = fmaxf(mx, e); s0 += e; }
-            for (int x = tail0; x < p.w; ++x) { const float e = row[x]; mn = fminf(mn, e); mx = fmaxf(mx, e); s1 += e; }
+        const float4 *vrow = reinterpret_cast<const float4 *>(row + head_n);
+        const int v0 = c * CHUNK_V + threadIdx.x;
+        float4 v[UNR];
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            const int i = v0 + k * RT;
+            // neutral element for lanes past the end of the row: min/max ignore +-inf halves, sum adds 0
+            v[k] = i < nvec ? __ldcs(vrow + i) : make_float4(INF, INF, INF, INF);
+        }
+#pragma unroll
+        for (int k = 0; k < UNR; ++k) {
+            if (v0 + k * RT < nvec) {
+                mn = fminf(mn, fminf(fminf(v[k].x, v[k].y), fminf(v[k].z, v[k].w)));
+                mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+                s0 += v[k].x; s1 += v[k].y; s2 += v[k].z; s3 += v[k].w;
+            }
+        }
+        if (c == 0) {  // scalar head / tail pixels of this row
+            const int nscal = head_n + (p.w - tail0);
+            for (int k = threadIdx.x; k < nscal; k += RT) {
+                const float e = row[k < head_n ? k : tail0 + (k - head_n)];
+                mn = fminf(mn, e); mx = fmaxf(mx, e); s0 += e;
+            }
         }
     }
     MMS v{mn, mx, ((double)s0 + (double)s1) + ((double)s2 + (double)s3)};
@@ -200,7 +220,10 @@ static int reduce_grid(long long units) {
 }
 
 static int launch_mms(const hb_view &v, void *result_dev, cudaStream_t s) {
-    const int blocks = reduce_grid(((long long)v.width / 4 + 1) * v.height);
+    const long long cpr = (v.width / 4 + CHUNK_V - 1) / CHUNK_V;
+    const long long chunks = (cpr < 1 ? 1 : cpr) * v.height;
+    const long long cap = (long long)sm_count() * 8;  // persistent: 8 CTAs of 256 threads per SM
+    const int blocks = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
     Scratch *sc = nullptr;
     int rc = get_scratch(&sc, blocks);
     if (rc) return rc;
