@@ -1,16 +1,22 @@
 // hb_bilateral.cu -- bilateral filter (the `iterate(dom, ...)` body of
 // samples-public/3_Preprocessing/Bilateral_Filter/src/main.cpp:63-77) for sm_100a.
 //
-// 169 exponentials per pixel at 13x13: this operator is bound by the MUFU (ex2) and FP32 issue
-// rate, not by HBM.  The tile + halo is staged once into shared memory as float; each
+// 169 exponentials per pixel at 13x13: this operator is bound by the MUFU pipe (ex2, 16 per clock per
+// SM), not by HBM.  The tile + halo is staged once into shared memory as float; each
 // thread owns 4 x 4 pixels and walks the staged rows once (row-stationary), so shared-memory
-// traffic is ~5 16-byte loads per 52 taps.  The per-pixel tap order (row-major) and the operation
-// sequence diff -> (-c_r*diff)*diff -> exp -> *mask -> d += s -> p += s*in follow the sample; the
-// exponential is ex2.approx on a pre-scaled argument (within the 1e-5 float contract, <= 1 LSB on
-// uchar where the sample itself tolerates |diff| <= 1).
+// traffic is ~5 16-byte loads per 52 taps.  The per-pixel tap order (row-major) follows the sample.
+// Per tap the sample computes  s = expf(-c_r*diff*diff) * mask ; d += s ; p += s*in.  To keep the FP32
+// pipe below the MUFU pipe the kernel evaluates the same value as
+//     s = ex2( (diff*diff) * (-c_r*log2 e) + log2(mask) )          (one FMA + one MUFU.EX2)
+//     d += s ; p = fma(s, in, p)
+// i.e. 5 FP32 instructions per tap instead of 9.  This is a float pipeline under the 1e-5 relative
+// contract (measured error vs libm ~1e-6, tests/test_gpu_parity.py); on uchar output a 1-LSB flip at
+// rounding ties is possible where the sample itself tolerates |diff| <= 1.  Masks with a non-positive
+// coefficient take the unfolded form  s = ex2(...) * mask.
 #include "hb_common.cuh"
 #include "hb_internal.h"
 
+#include <cmath>
 #include <cstring>
 
 namespace hb {
@@ -22,14 +28,20 @@ struct BilateralParams {
     Window win;
     int in_ox, in_oy;
     int out_stride, out_ox, out_oy, is_w, is_h;
-    float neg_cr;  // -c_r
+    float k2;      // -c_r * log2(e)
     float cval;
-    float coef[169];
+    float coef[169];  // FOLD: log2(mask), else mask
 };
 
 constexpr int BTW = 128, BRPT = 4, BBX = 32, BBY = 8, BTH = BBY * BRPT;
 
-template <typename T, int S>
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <typename T, int S, bool FOLD>
 __global__ void __launch_bounds__(BBX *BBY) bilateral_kernel(const __grid_constant__ BilateralParams p) {
     constexpr int H = S / 2;
     constexpr int HXP = round_up(H, 4);
@@ -55,7 +67,7 @@ __global__ void __launch_bounds__(BBX *BBY) bilateral_kernel(const __grid_consta
             psum[r][i] = 0.0f;
         }
 
-    const float LOG2E = 1.4426950408889634f;
+    const float k2 = p.k2;
 #pragma unroll 1
     for (int ir = 0; ir < BRPT + S - 1; ++ir) {
         float w[WIN];
@@ -77,11 +89,15 @@ __global__ void __launch_bounds__(BBX *BBY) bilateral_kernel(const __grid_consta
                 for (int i = 0; i < 4; ++i) {
                     const float v = w[HXP - H + i + dx];
                     const float diff = __fadd_rn(v, -center[r][i]);
-                    const float arg = __fmul_rn(__fmul_rn(p.neg_cr, diff), diff);  // (-c_r*diff)*diff
-                    const float e = exp2f(__fmul_rn(arg, LOG2E));                  // ex2.approx (see header)
-                    const float s = __fmul_rn(e, m);
+                    const float t = __fmul_rn(diff, diff);
+                    float s;
+                    if (FOLD) {
+                        s = ex2_approx(__fmaf_rn(t, k2, m));
+                    } else {
+                        s = __fmul_rn(ex2_approx(__fmul_rn(t, k2)), m);
+                    }
                     dsum[r][i] = __fadd_rn(dsum[r][i], s);
-                    psum[r][i] = __fadd_rn(psum[r][i], __fmul_rn(s, v));
+                    psum[r][i] = __fmaf_rn(s, v, psum[r][i]);
                 }
             }
         }
@@ -111,27 +127,33 @@ __global__ void __launch_bounds__(BBX *BBY) bilateral_kernel(const __grid_consta
     }
 }
 
-template <typename T, int S>
-static void launch_bilateral(const BilateralParams &p, cudaStream_t s) {
+template <typename T, int S, bool FOLD>
+static void launch_bilateral_v(const BilateralParams &p, cudaStream_t s) {
     constexpr int HXP = round_up(S / 2, 4);
     constexpr size_t smem = (size_t)(BTH + S - 1) * (BTW + 2 * HXP) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(bilateral_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(bilateral_kernel<T, S, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
     dim3 grid((p.is_w + BTW - 1) / BTW, (p.is_h + BTH - 1) / BTH);
-    bilateral_kernel<T, S><<<grid, dim3(BBX, BBY), smem, s>>>(p);
+    bilateral_kernel<T, S, FOLD><<<grid, dim3(BBX, BBY), smem, s>>>(p);
     g_launches++;
 }
 
+template <typename T, int S>
+static void launch_bilateral(const BilateralParams &p, bool fold, cudaStream_t s) {
+    if (fold) launch_bilateral_v<T, S, true>(p, s);
+    else launch_bilateral_v<T, S, false>(p, s);
+}
+
 template <typename T>
-static int dispatch_bilateral(const BilateralParams &p, int size, cudaStream_t s) {
+static int dispatch_bilateral(const BilateralParams &p, int size, bool fold, cudaStream_t s) {
     switch (size) {
-    case 3: launch_bilateral<T, 3>(p, s); return HB_OK;
-    case 5: launch_bilateral<T, 5>(p, s); return HB_OK;
-    case 7: launch_bilateral<T, 7>(p, s); return HB_OK;
-    case 13: launch_bilateral<T, 13>(p, s); return HB_OK;
+    case 3: launch_bilateral<T, 3>(p, fold, s); return HB_OK;
+    case 5: launch_bilateral<T, 5>(p, fold, s); return HB_OK;
+    case 7: launch_bilateral<T, 7>(p, fold, s); return HB_OK;
+    case 13: launch_bilateral<T, 13>(p, fold, s); return HB_OK;
     default: return HB_ERR_UNSUPPORTED;
     }
 }
@@ -152,18 +174,21 @@ extern "C" int hb_bilateral(const hb_bilateral_desc *d, void *stream) {
     p.win = Window{in.offset_x, in.offset_x + in.width, in.offset_y - in.ghost_top, in.offset_y + in.height + in.ghost_bottom, d->boundary};
     p.in_ox = in.offset_x; p.in_oy = in.offset_y;
     p.out_stride = out.stride; p.out_ox = out.offset_x; p.out_oy = out.offset_y; p.is_w = out.width; p.is_h = out.height;
-    p.neg_cr = -(0.5f / (float)(d->sigma_r * d->sigma_r));  // float c_r = 0.5f/(sigma_r*sigma_r)
+    const float c_r = 0.5f / (float)(d->sigma_r * d->sigma_r);  // float c_r = 0.5f/(sigma_r*sigma_r)
+    p.k2 = (float)(-(double)c_r * 1.4426950408889634);
     p.cval = (float)d->boundary_const;
     if (d->size * d->size > 169 || d->size <= 0) {
         log_msg(2, "hb_bilateral: mask size %d unsupported", d->size);
         return HB_ERR_UNSUPPORTED;
     }
-    for (int k = 0; k < d->size * d->size; ++k) p.coef[k] = d->coef_f32[k];
+    bool fold = true;
+    for (int k = 0; k < d->size * d->size; ++k) fold = fold && d->coef_f32[k] > 0.0f;
+    for (int k = 0; k < d->size * d->size; ++k) p.coef[k] = fold ? (float)log2((double)d->coef_f32[k]) : d->coef_f32[k];
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_bilateral");
     int rc = HB_ERR_UNSUPPORTED;
-    if (in.dtype == HB_U8) rc = dispatch_bilateral<uchar>(p, d->size, s);
-    else if (in.dtype == HB_F32) rc = dispatch_bilateral<float>(p, d->size, s);
+    if (in.dtype == HB_U8) rc = dispatch_bilateral<uchar>(p, d->size, fold, s);
+    else if (in.dtype == HB_F32) rc = dispatch_bilateral<float>(p, d->size, fold, s);
     HB_REQUIRE(rc == HB_OK, HB_ERR_UNSUPPORTED, "hb_bilateral: no device kernel for dtype %d size %d (sizes 3,5,7,13; u8/f32); no CPU fallback",
                in.dtype, d->size);
     return scope.finish();

@@ -1,0 +1,179 @@
+// hb_binning.cu -- binning / histograms (Kernel::binning() + binned_data(), dsl/kernel.hpp:163-209) for sm_100a.
+//
+// Replaces hipaccApplyBinningSegmented and the generated segmented-binning kernel
+// (runtime/hipacc_cu.tpp:410-464, runtime/hipacc_cu_red.hpp:527-641: per-warp hand-rolled locks in
+// shared memory, a second merge kernel, cudaMalloc/cudaFree per call).
+//
+// One pass over HBM (4 B per float pixel, 1 B per uchar pixel): a persistent grid walks row chunks with
+// 16-byte streaming loads (4 independent loads in flight per thread); every warp owns a private copy of
+// the bins in shared memory (native shared-memory atomics, no cross-warp contention); at the end the
+// CTA folds its copies and adds the non-zero bins to the result with global atomics.  Integer addition
+// commutes, so the result does not depend on the schedule.
+#include "hb_common.cuh"
+#include "hb_internal.h"
+
+#include <cstring>
+
+namespace hb {
+
+struct BinParams {
+    const void *in;
+    int stride, w, h, ox, oy;
+    unsigned *bins;
+    int num_bins, copies;  // copies of the bins in shared memory (0: global atomics only)
+    int index_kind, value_kind;
+    float p0, nbf;
+};
+
+constexpr int HT = 256, HU = 4;
+
+template <typename T> struct BinVec;
+template <> struct BinVec<float> { typedef float4 V; static constexpr int N = 4; };
+template <> struct BinVec<uchar> { typedef uint4 V; static constexpr int N = 16; };
+
+__device__ __forceinline__ void unpack(const float4 &v, float (&e)[4]) { e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; }
+__device__ __forceinline__ void unpack(const uint4 &v, uchar (&e)[16]) {
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = (uchar)(w[i >> 2] >> (8 * (i & 3)));
+}
+
+// C `(uint)f` as g++ / x86-64 evaluates it: truncate through 64 bits, keep the low 32
+__device__ __forceinline__ unsigned f2u_c(float f) { return (unsigned)__float2ll_rz(f); }
+
+template <typename T>
+__device__ __forceinline__ void bin_put(const BinParams &p, unsigned *sh, T e) {
+    unsigned idx, val;
+    if (DtypeOf<T>::v == HB_F32) {
+        idx = p.index_kind == HB_BIN_INDEX_SCALE ? f2u_c(__fmul_rn(__fdiv_rn((float)e, p.p0), p.nbf)) : f2u_c((float)e);
+        val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : f2u_c((float)e);
+    } else {
+        idx = p.index_kind == HB_BIN_INDEX_SCALE ? f2u_c(__fmul_rn(__fdiv_rn((float)e, p.p0), p.nbf)) : (unsigned)e;
+        val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : (unsigned)e;
+    }
+    if (idx < (unsigned)p.num_bins) {
+        if (sh) atomicAdd(sh + idx, val);
+        else atomicAdd(p.bins + idx, val);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ BinParams p) {
+    typedef typename BinVec<T>::V V;
+    constexpr int N = BinVec<T>::N;
+    extern __shared__ unsigned hsh[];
+    for (int i = threadIdx.x; i < p.copies * p.num_bins; i += HT) hsh[i] = 0u;
+    __syncthreads();
+    unsigned *my = p.copies ? hsh + ((threadIdx.x >> 5) % p.copies) * p.num_bins : nullptr;
+
+    const T *in = static_cast<const T *>(p.in);
+    const uintptr_t base_addr = reinterpret_cast<uintptr_t>(in) + (size_t)p.ox * sizeof(T);
+    const bool aligned_rows = ((size_t)p.stride * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0;
+    const int head = aligned_rows ? (int)(((16 - (base_addr & 15)) & 15) / sizeof(T)) : 0;  // scalar pixels before alignment
+    const int head_n = head < p.w ? head : p.w;
+    const int nvec = aligned_rows ? (p.w - head_n) / N : 0;
+    const int tail0 = head_n + nvec * N;
+    const int cpr = nvec > 0 ? (nvec + HT * HU - 1) / (HT * HU) : 1;
+    const long long total = (long long)cpr * p.h;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int y = (int)(u / cpr), c = (int)(u - (long long)y * cpr);
+        const T *row = in + (size_t)(p.oy + y) * p.stride + p.ox;
+        const V *vrow = reinterpret_cast<const V *>(row + head_n);
+        const int v0 = c * (HT * HU) + threadIdx.x;
+        V v[HU];
+#pragma unroll
+        for (int k = 0; k < HU; ++k)
+            if (v0 + k * HT < nvec) v[k] = __ldcs(vrow + v0 + k * HT);
+#pragma unroll
+        for (int k = 0; k < HU; ++k)
+            if (v0 + k * HT < nvec) {
+                T e[N];
+                unpack(v[k], e);
+#pragma unroll
+                for (int i = 0; i < N; ++i) bin_put<T>(p, my, e[i]);
+            }
+        if (c == 0) {  // scalar head / tail pixels of this row
+            const int nscal = head_n + (p.w - tail0);
+            for (int k = threadIdx.x; k < nscal; k += HT) bin_put<T>(p, my, row[k < head_n ? k : tail0 + (k - head_n)]);
+        }
+    }
+    if (p.copies) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.num_bins; i += HT) {
+            unsigned a = 0;
+            for (int k = 0; k < p.copies; ++k) a += hsh[k * p.num_bins + i];
+            if (a) atomicAdd(p.bins + i, a);
+        }
+    }
+}
+
+struct BinScratch {
+    unsigned *dev = nullptr, *host = nullptr;
+    int cap = 0;
+};
+static BinScratch g_bin[16];
+
+static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStream_t s, const char *who) {
+    hb_view v = norm_view(d->in);
+    HB_REQUIRE(view_ok(v) && (v.dtype == HB_F32 || v.dtype == HB_U8), HB_ERR_UNSUPPORTED, "%s: needs a valid f32 or u8 view; no CPU fallback", who);
+    HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 24), HB_ERR_INVALID, "%s: num_bins %d out of range", who, d->num_bins);
+    HB_REQUIRE(d->index_kind == HB_BIN_INDEX_SCALE || d->index_kind == HB_BIN_INDEX_PIXEL, HB_ERR_INVALID, "%s: bad index kind", who);
+    HB_REQUIRE(d->value_kind == HB_BIN_VALUE_ONE || d->value_kind == HB_BIN_VALUE_PIXEL, HB_ERR_INVALID, "%s: bad value kind", who);
+    HB_REQUIRE(d->index_kind != HB_BIN_INDEX_SCALE || d->p0 != 0.0, HB_ERR_INVALID, "%s: p0 == 0", who);
+    BinParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = v.data; p.stride = v.stride; p.w = v.width; p.h = v.height; p.ox = v.offset_x; p.oy = v.offset_y;
+    p.bins = bins_dev; p.num_bins = d->num_bins; p.index_kind = d->index_kind; p.value_kind = d->value_kind;
+    p.p0 = (float)d->p0; p.nbf = (float)(unsigned)d->num_bins;
+    const int max_words = 48 * 1024 / 4;
+    p.copies = d->num_bins > max_words ? 0 : (max_words / d->num_bins < HT / 32 ? max_words / d->num_bins : HT / 32);
+    const size_t smem = (size_t)p.copies * d->num_bins * sizeof(unsigned);
+    const int npv = v.dtype == HB_F32 ? 4 : 16;
+    const long long cpr = (v.width / npv + HT * HU - 1) / (HT * HU);
+    const long long chunks = (cpr < 1 ? 1 : cpr) * v.height;
+    const long long cap = (long long)sm_count() * (smem > 16 * 1024 ? 4 : 8);
+    const int blocks = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+    int rc = check_cuda(cudaMemsetAsync(bins_dev, 0, sizeof(unsigned) * d->num_bins, s), "cudaMemsetAsync(bins)");
+    if (rc) return rc;
+    if (v.dtype == HB_F32) binning_kernel<float><<<blocks, HT, smem, s>>>(p);
+    else binning_kernel<uchar><<<blocks, HT, smem, s>>>(p);
+    g_launches++;
+    return HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" int hb_binning_async(const hb_binning_desc *d, uint32_t *bins_device, void *stream) {
+    HB_REQUIRE(d && bins_device, HB_ERR_INVALID, "hb_binning_async: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    OpScope scope(s, "hb_binning_async");
+    int rc = launch_binning(d, bins_device, s, "hb_binning_async");
+    if (rc) return rc;
+    return scope.finish();
+}
+
+extern "C" int hb_binning(const hb_binning_desc *d, uint32_t *bins_host, void *stream) {
+    HB_REQUIRE(d && bins_host, HB_ERR_INVALID, "hb_binning: null argument");
+    HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 24), HB_ERR_INVALID, "hb_binning: num_bins %d out of range", d->num_bins);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    BinScratch &sc = g_bin[dev & 15];
+    if (sc.cap < d->num_bins) {
+        if (sc.dev) { cudaFree(sc.dev); cudaFreeHost(sc.host); sc.dev = nullptr; sc.host = nullptr; sc.cap = 0; }
+        int rc = check_cuda(cudaMalloc(&sc.dev, sizeof(unsigned) * d->num_bins), "cudaMalloc(bins)");
+        rc |= check_cuda(cudaMallocHost(&sc.host, sizeof(unsigned) * d->num_bins), "cudaMallocHost(bins)");
+        if (rc) return rc;
+        sc.cap = d->num_bins;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    OpScope scope(s, "hb_binning");
+    int rc = launch_binning(d, sc.dev, s, "hb_binning");
+    if (rc) return rc;
+    rc = scope.finish();
+    rc |= check_cuda(cudaMemcpyAsync(sc.host, sc.dev, sizeof(unsigned) * d->num_bins, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(bins)");
+    rc |= check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize()");  // blocking like the reference
+    memcpy(bins_host, sc.host, sizeof(unsigned) * d->num_bins);
+    return rc ? HB_ERR_CUDA : HB_OK;
+}

@@ -94,47 +94,114 @@ __device__ __forceinline__ TO point_eval(int op, TI a, TI b, TI c, const PointPa
     }
 }
 
-template <typename TI, typename TO, bool VEC>
+// Scalar / interpolating path: 4 pixels per thread, every pixel through the accessor (NN / LF, tails, unaligned rows).
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) point_kernel(const __grid_constant__ PointParams p) {
     const int vw = (p.is_w + 3) / 4;  // 4-pixel groups per row
     const long long total = (long long)vw * p.is_h;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         const int gy = (int)(g / vw), gx = (int)(g - (long long)gy * vw) * 4;
         TI v[3][4];
-        if (VEC && gx + 3 < p.is_w) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (k < p.n_in) load4(static_cast<const TI *>(p.in[k].p) + (size_t)(p.in[k].oy + gy) * p.in[k].stride + p.in[k].ox + gx, v[k]);
-        } else {
+        for (int k = 0; k < 3; ++k)
+            if (k < p.n_in)
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (k < p.n_in)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[k][i] = gx + i < p.is_w ? fetch_interp<TI>(p.in[k], gx + i, gy, p.is_w, p.is_h) : TI(0);
-        }
-        TO o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = point_eval<TI, TO>(p.op, v[0][i], p.n_in > 1 ? v[1][i] : TI(0), p.n_in > 2 ? v[2][i] : TI(0), p);
+                for (int i = 0; i < 4; ++i) v[k][i] = gx + i < p.is_w ? fetch_interp<TI>(p.in[k], gx + i, gy, p.is_w, p.is_h) : TI(0);
         TO *dst = static_cast<TO *>(p.out) + (size_t)(p.out_oy + gy) * p.out_stride + p.out_ox + gx;
-        if (VEC && gx + 3 < p.is_w) {
-            store4(dst, o);
-        } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (gx + i < p.is_w) dst[i] = o[i];
+        for (int i = 0; i < 4; ++i)
+            if (gx + i < p.is_w) dst[i] = point_eval<TI, TO>(p.op, v[0][i], p.n_in > 1 ? v[1][i] : TI(0), p.n_in > 2 ? v[2][i] : TI(0), p);
+    }
+}
+
+// Streaming path (no interpolation, 4-pixel aligned rows): a persistent grid walks row chunks of PT x PU
+// 4-pixel vectors; every thread first issues its PU independent vector loads per input (PU x NIN x 16 bytes
+// in flight for float), then evaluates and stores.  OP and NIN are compile-time so the body is straight-line.
+constexpr int PT = 256, PU = 4;
+
+template <typename T> __device__ __forceinline__ void load4_stream(const T *p, T (&v)[4]) {
+    typedef typename Vec4<T>::type V;
+    V t = __ldcs(reinterpret_cast<const V *>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <typename T> __device__ __forceinline__ void store4_stream(T *p, const T (&v)[4]) {
+    typedef typename Vec4<T>::type V;
+    V t;
+    t.x = v[0]; t.y = v[1]; t.z = v[2]; t.w = v[3];
+    __stcs(reinterpret_cast<V *>(p), t);
+}
+
+template <typename TI, typename TO, int OP, int NIN>
+__global__ void __launch_bounds__(PT) point_stream_kernel(const __grid_constant__ PointParams p) {
+    const int nvec = p.is_w / 4;                       // full vectors per row
+    const int tail0 = nvec * 4;
+    const int cpr = nvec > 0 ? (nvec + PT * PU - 1) / (PT * PU) : 1;
+    const long long total = (long long)cpr * p.is_h;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int gy = (int)(u / cpr), c = (int)(u - (long long)gy * cpr);
+        const TI *row[NIN];
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) row[k] = static_cast<const TI *>(p.in[k].p) + (size_t)(p.in[k].oy + gy) * p.in[k].stride + p.in[k].ox;
+        TO *orow = static_cast<TO *>(p.out) + (size_t)(p.out_oy + gy) * p.out_stride + p.out_ox;
+        const int v0 = c * (PT * PU) + threadIdx.x;
+        TI v[PU][3][4];
+#pragma unroll
+        for (int j = 0; j < PU; ++j) {
+            const int i = v0 + j * PT;
+            if (i < nvec) {
+#pragma unroll
+                for (int k = 0; k < NIN; ++k) load4_stream(row[k] + 4 * i, v[j][k]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PU; ++j) {
+            const int i = v0 + j * PT;
+            if (i < nvec) {
+                TO o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    o[q] = point_eval<TI, TO>(OP, v[j][0][q], NIN > 1 ? v[j][NIN > 1 ? 1 : 0][q] : TI(0), NIN > 2 ? v[j][NIN > 2 ? 2 : 0][q] : TI(0), p);
+                store4_stream(orow + 4 * i, o);
+            }
+        }
+        if (c == 0 && threadIdx.x < p.is_w - tail0) {  // the row's last (is_w % 4) pixels
+            const int x = tail0 + threadIdx.x;
+            orow[x] = point_eval<TI, TO>(OP, row[0][x], NIN > 1 ? row[NIN > 1 ? 1 : 0][x] : TI(0), NIN > 2 ? row[NIN > 2 ? 2 : 0][x] : TI(0), p);
         }
     }
 }
 
+template <typename TI, typename TO, int OP, int NIN>
+static void launch_stream(const PointParams &p, cudaStream_t s) {
+    const int nvec = p.is_w / 4;
+    const int cpr = nvec > 0 ? (nvec + PT * PU - 1) / (PT * PU) : 1;
+    long long blocks = (long long)cpr * p.is_h;
+    const long long cap = (long long)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    point_stream_kernel<TI, TO, OP, NIN><<<(unsigned)blocks, PT, 0, s>>>(p);
+}
+
 template <typename TI, typename TO>
 static int launch_point(const PointParams &p, bool vec, cudaStream_t s) {
-    const long long total = (long long)((p.is_w + 3) / 4) * p.is_h;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)sm_count() * 32;  // grid-stride beyond a few waves
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    if (vec) point_kernel<TI, TO, true><<<(unsigned)blocks, 256, 0, s>>>(p);
-    else point_kernel<TI, TO, false><<<(unsigned)blocks, 256, 0, s>>>(p);
+    if (vec) {
+        switch (p.op) {
+        case HB_POINT_COPY: launch_stream<TI, TO, HB_POINT_COPY, 1>(p, s); break;
+        case HB_POINT_SQUARE: launch_stream<TI, TO, HB_POINT_SQUARE, 1>(p, s); break;
+        case HB_POINT_MUL: launch_stream<TI, TO, HB_POINT_MUL, 2>(p, s); break;
+        case HB_POINT_SUB: launch_stream<TI, TO, HB_POINT_SUB, 2>(p, s); break;
+        case HB_POINT_ADD: launch_stream<TI, TO, HB_POINT_ADD, 2>(p, s); break;
+        case HB_POINT_BLEND: launch_stream<TI, TO, HB_POINT_BLEND, 2>(p, s); break;
+        case HB_POINT_SOBEL_COMBINE: launch_stream<TI, TO, HB_POINT_SOBEL_COMBINE, 2>(p, s); break;
+        default: launch_stream<TI, TO, HB_POINT_HARRIS, 3>(p, s); break;
+        }
+    } else {
+        const long long total = (long long)((p.is_w + 3) / 4) * p.is_h;
+        long long blocks = (total + 255) / 256;
+        const long long cap = (long long)sm_count() * 32;  // grid-stride beyond a few waves
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        point_kernel<TI, TO><<<(unsigned)blocks, 256, 0, s>>>(p);
+    }
     g_launches++;
     return HB_OK;
 }

@@ -120,6 +120,277 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const __grid_constant__ Pyr
     }
 }
 
+
+// ================================================================================================
+// Exact-halving transitions (fine = 2 x coarse in both dimensions, the case of every level of a
+// power-of-two pyramid): the accessor strides are exactly 2 (NN) and 0.5 (LF), so the float mapping
+// of dsl/image.hpp:390-422 collapses to integers with exact weights:
+//   NN : coarse (cx,cy) samples fine (2cx+1, 2cy+1)
+//   LF : fine x = 2m   (m > 0): x_int = m-1, xf = 0.75 ;  x = 0: x_int = 0, xf = 0 (x_mapped-0.5 clamps at 0)
+//        fine x = 2m+1        : x_int = m,   xf = 0.25 ;  neighbour x_int+1 through CLAMP
+// (0.25 + 0.5*x, the subtraction of 0.5 and the weight products are all exact in float, so using the
+// constants is bit-identical to evaluating the general formula.)  The sum keeps the DSL's order:
+// ((omx*omy)*p00 + (xf*omy)*p10) + (omx*yf)*p01) + (xf*yf)*p11.
+// ================================================================================================
+
+// generic (edge-safe) bilinear sample for the exact-halving case; `at(cx,cy)` returns the coarse value
+template <typename F>
+__device__ __forceinline__ float lf_half(F at, int x, int y, int cw, int ch) {
+    int x0, x1, y0, y1;
+    float xf, yf;
+    if (x & 1) { x0 = x >> 1; x1 = min(x0 + 1, cw - 1); xf = 0.25f; }
+    else if (x == 0) { x0 = 0; x1 = min(1, cw - 1); xf = 0.0f; }
+    else { x0 = (x >> 1) - 1; x1 = x0 + 1; xf = 0.75f; }
+    if (y & 1) { y0 = y >> 1; y1 = min(y0 + 1, ch - 1); yf = 0.25f; }
+    else if (y == 0) { y0 = 0; y1 = min(1, ch - 1); yf = 0.0f; }
+    else { y0 = (y >> 1) - 1; y1 = y0 + 1; yf = 0.75f; }
+    const float omx = __fadd_rn(1.0f, -xf), omy = __fadd_rn(1.0f, -yf);
+    float r = __fmul_rn(__fmul_rn(omx, omy), at(x0, y0));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(xf, omy), at(x1, y0)));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(omx, yf), at(x0, y1)));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(xf, yf), at(x1, y1)));
+    return r;
+}
+
+// Interior fast path: c[j][i] = coarse(m-1+i, k-1+j) for the thread's 4x4 fine block at (2m, 2k), m,k >= 1 (or
+// clamped duplicates at the right / bottom edge).  Pixel (i,j) of the block uses columns (i+1)/2, (i+1)/2+1 and
+// rows (j+1)/2, (j+1)/2+1 with weights (0.25,0.75) for even and (0.75,0.25) for odd offsets.
+__device__ __forceinline__ float lf_block(const float (&c)[4][4], int i, int j) {
+    const int ci = (i + 1) >> 1, cj = (j + 1) >> 1;
+    const float xf = (i & 1) ? 0.25f : 0.75f, yf = (j & 1) ? 0.25f : 0.75f;
+    const float omx = 1.0f - xf, omy = 1.0f - yf;   // exact
+    float r = __fmul_rn(omx * omy, c[cj][ci]);      // weight products are exact constants
+    r = __fadd_rn(r, __fmul_rn(xf * omy, c[cj][ci + 1]));
+    r = __fadd_rn(r, __fmul_rn(omx * yf, c[cj + 1][ci]));
+    r = __fadd_rn(r, __fmul_rn(xf * yf, c[cj + 1][ci + 1]));
+    return r;
+}
+
+constexpr int FD_TW = 128, FD_TH = 32;                 // fine tile of one CTA
+constexpr int FD_CCOLS = 68, FD_CROWS = 18;            // coarse tile incl. halo 1 (66 used columns, computed as 34 pairs)
+constexpr int FD_FCOLS = 144;                          // staged fine columns (column 0 <-> x = X0 - 4)
+constexpr int FD_NT = 256;
+
+struct PyrFusedParams {
+    const float *fine;
+    float *coarse, *lap;
+    int fine_stride, coarse_stride, lap_stride;
+    int fw, fh, cw, ch;
+    float coef[49];
+};
+
+// blur(fine) sampled at (2cx+1, 2cy+1) -> coarse, and lap = fine - LF(coarse), one pass: 4 B read + 1 B + 4 B
+// written per fine pixel (the unfused sequence moves 19).  Phase 1 computes the coarse tile with a 1-pixel halo
+// (the halo is recomputed by the neighbouring CTAs, 16 % extra FP work) from the staged fine tile: each thread
+// owns 2 coarse columns x 3 coarse rows and walks the S+4 fine rows once (row-stationary, 16-byte LDS).  Phase 2
+// is the DoG on 4x4 fine blocks from the two tiles.
+template <int S>
+__global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_constant__ PyrFusedParams p) {
+    constexpr int H = S / 2;
+    constexpr int FROWS = 35 + 2 * H;                  // row 0 <-> y = Y0 - 1 - H
+    __shared__ __align__(16) float ftile[FROWS * FD_FCOLS];
+    __shared__ __align__(16) float ctile[FD_CROWS * FD_CCOLS];  // (0,0) <-> coarse (CX0-1, CY0-1)
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * FD_TW, Y0 = blockIdx.y * FD_TH;
+    const int CX0 = X0 >> 1, CY0 = Y0 >> 1;
+
+    // ---- stage the fine tile, CLAMP applied here (Gaussian's BoundaryCondition), so phase 1 is branch-free
+    {
+        constexpr int VPR = FD_FCOLS / 4;
+        const int xs = X0 - 4, ys = Y0 - 1 - H;
+        for (int v = tid; v < FROWS * VPR; v += FD_NT) {
+            const int r = v / VPR, c4 = v - r * VPR;
+            const int gy = min(max(ys + r, 0), p.fh - 1);
+            const int gx = xs + 4 * c4;
+            const float *row = p.fine + (size_t)gy * p.fine_stride;
+            float4 t;
+            if (gx >= 0 && gx + 3 < p.fw) {
+                t = __ldg(reinterpret_cast<const float4 *>(row + gx));
+            } else {
+                t.x = __ldg(row + min(max(gx, 0), p.fw - 1));
+                t.y = __ldg(row + min(max(gx + 1, 0), p.fw - 1));
+                t.z = __ldg(row + min(max(gx + 2, 0), p.fw - 1));
+                t.w = __ldg(row + min(max(gx + 3, 0), p.fw - 1));
+            }
+            *reinterpret_cast<float4 *>(ftile + r * FD_FCOLS + 4 * c4) = t;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: coarse tile.  thread -> column pair pc (coarse tile columns 2pc, 2pc+1), row group rg (3 rows)
+    if (tid < 34 * 6) {
+        const int pc = tid % 34, rg = tid / 34;
+        float acc[3][2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j][0] = acc[j][1] = 0.0f;
+#pragma unroll
+        for (int fr = 0; fr < S + 4; ++fr) {
+            float w[12];
+            const float *row = ftile + (6 * rg + fr) * FD_FCOLS + 4 * pc;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float4 t = *reinterpret_cast<const float4 *>(row + 4 * q);
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int dy = fr - 2 * j;
+                if (dy < 0 || dy >= S) continue;
+#pragma unroll
+                for (int dx = 0; dx < S; ++dx) {
+                    const float cf = p.coef[dy * S + dx];
+                    acc[j][0] = __fadd_rn(acc[j][0], __fmul_rn(w[3 - H + dx], cf));
+                    acc[j][1] = __fadd_rn(acc[j][1], __fmul_rn(w[5 - H + dx], cf));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int tr = 3 * rg + j;
+            *reinterpret_cast<float2 *>(ctile + tr * FD_CCOLS + 2 * pc) = make_float2(acc[j][0], acc[j][1]);
+            const int cy = CY0 - 1 + tr;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int tc = 2 * pc + e, cx = CX0 - 1 + tc;
+                if (tc >= 1 && tc <= FD_TW / 2 && tr >= 1 && tr <= FD_TH / 2 && cx < p.cw && cy < p.ch)
+                    p.coarse[(size_t)cy * p.coarse_stride + cx] = acc[j][e];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: lap = fine - LF(coarse) on the thread's 4 x 4 fine block
+    const int tx = tid & 31, ty = tid >> 5;
+    const int x = X0 + 4 * tx, y = Y0 + 4 * ty;
+    if (x >= p.fw || y >= p.fh) return;
+    const bool edge = X0 == 0 || Y0 == 0 || X0 + FD_TW >= p.fw || Y0 + FD_TH >= p.fh;
+    float o[4][4];
+    if (!edge) {
+        float c[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 a = *reinterpret_cast<const float2 *>(ctile + (2 * ty + j) * FD_CCOLS + 2 * tx);
+            const float2 b = *reinterpret_cast<const float2 *>(ctile + (2 * ty + j) * FD_CCOLS + 2 * tx + 2);
+            c[j][0] = a.x; c[j][1] = a.y; c[j][2] = b.x; c[j][3] = b.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 f = *reinterpret_cast<const float4 *>(ftile + (4 * ty + j + 1 + H) * FD_FCOLS + 4 + 4 * tx);
+            o[j][0] = __fadd_rn(f.x, -lf_block(c, 0, j));
+            o[j][1] = __fadd_rn(f.y, -lf_block(c, 1, j));
+            o[j][2] = __fadd_rn(f.z, -lf_block(c, 2, j));
+            o[j][3] = __fadd_rn(f.w, -lf_block(c, 3, j));
+        }
+    } else {
+        auto at = [&](int cx, int cy) { return ctile[(cy - CY0 + 1) * FD_CCOLS + (cx - CX0 + 1)]; };
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
+                const float f = ftile[(yy - Y0 + 1 + H) * FD_FCOLS + 4 + (xx - X0)];
+                o[j][i] = __fadd_rn(f, -lf_half(at, xx, yy, p.cw, p.ch));
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (y + j >= p.fh) break;
+        float *dst = p.lap + (size_t)(y + j) * p.lap_stride + x;
+        if (x + 3 < p.fw) {
+            __stcs(reinterpret_cast<float4 *>(dst), make_float4(o[j][0], o[j][1], o[j][2], o[j][3]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < p.fw) dst[i] = o[j][i];
+        }
+    }
+}
+
+struct PyrUpHalfParams {
+    const float *cg, *cl;
+    float *fg, *fl;
+    int cg_stride, cl_stride, fg_stride, fl_stride;
+    int fw, fh, cw, ch;
+};
+
+// Restore + Blend for the exact-halving case: 4 x 4 fine block per thread, the two 4 x 4 coarse neighbourhoods
+// come through the read-only path (each coarse value is used by ~16 fine pixels: L1/L2 hits), lap is read once
+// with 16-byte streaming loads, both outputs are written with 16-byte stores.
+__global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant__ PyrUpHalfParams p) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * 128 + 4 * tx, y = blockIdx.y * 32 + 4 * ty;
+    if (x >= p.fw || y >= p.fh) return;
+    float l[4][4], og[4][4], ol[4][4];
+    const bool full = x + 3 < p.fw && y + 3 < p.fh;
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(p.fl + (size_t)(y + j) * p.fl_stride + x));
+            l[j][0] = t.x; l[j][1] = t.y; l[j][2] = t.z; l[j][3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) l[j][i] = p.fl[(size_t)min(y + j, p.fh - 1) * p.fl_stride + min(x + i, p.fw - 1)];
+    }
+    if (full && x > 0 && y > 0) {
+        const int m = x >> 1, k = y >> 1;
+        float g[4][4], c[4][4];
+        const int c0 = m - 1, c3 = min(m + 2, p.cw - 1), c2 = min(m + 1, p.cw - 1);  // m even: (m, m+1) is an 8-byte aligned pair
+        const bool pair = (p.cg_stride % 2 == 0) && (p.cl_stride % 2 == 0) && m + 1 < p.cw &&
+                          ((reinterpret_cast<uintptr_t>(p.cg) | reinterpret_cast<uintptr_t>(p.cl)) % 8 == 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cy = min(k - 1 + j, p.ch - 1);
+            const float *rg = p.cg + (size_t)cy * p.cg_stride, *rl = p.cl + (size_t)cy * p.cl_stride;
+            g[j][0] = __ldg(rg + c0); c[j][0] = __ldg(rl + c0);
+            if (pair) {
+                const float2 a = __ldg(reinterpret_cast<const float2 *>(rg + m)), b = __ldg(reinterpret_cast<const float2 *>(rl + m));
+                g[j][1] = a.x; g[j][2] = a.y; c[j][1] = b.x; c[j][2] = b.y;
+            } else {
+                g[j][1] = __ldg(rg + m); g[j][2] = __ldg(rg + c2); c[j][1] = __ldg(rl + m); c[j][2] = __ldg(rl + c2);
+            }
+            g[j][3] = __ldg(rg + c3); c[j][3] = __ldg(rl + c3);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                og[j][i] = __fadd_rn(lf_block(g, i, j), l[j][i]);
+                ol[j][i] = __fadd_rn(lf_block(c, i, j), __fdiv_rn(l[j][i], 2.0f));
+            }
+    } else {
+        auto atg = [&](int cx, int cy) { return __ldg(p.cg + (size_t)cy * p.cg_stride + cx); };
+        auto atl = [&](int cx, int cy) { return __ldg(p.cl + (size_t)cy * p.cl_stride + cx); };
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
+                og[j][i] = __fadd_rn(lf_half(atg, xx, yy, p.cw, p.ch), l[j][i]);
+                ol[j][i] = __fadd_rn(lf_half(atl, xx, yy, p.cw, p.ch), __fdiv_rn(l[j][i], 2.0f));
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (y + j >= p.fh) break;
+        float *dg = p.fg + (size_t)(y + j) * p.fg_stride + x, *dl = p.fl + (size_t)(y + j) * p.fl_stride + x;
+        if (x + 3 < p.fw) {
+            __stcs(reinterpret_cast<float4 *>(dg), make_float4(og[j][0], og[j][1], og[j][2], og[j][3]));
+            __stcs(reinterpret_cast<float4 *>(dl), make_float4(ol[j][0], ol[j][1], ol[j][2], ol[j][3]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < p.fw) { dg[i] = og[j][i]; dl[i] = ol[j][i]; }
+        }
+    }
+}
+
+// region base pointer + alignment test of a plane for the 16-byte paths
+static inline float *region_base(const PlaneRef &r) { return r.p + (size_t)r.oy * r.stride + r.ox; }
+static inline bool vec_ok(const PlaneRef &r) { return r.stride % 4 == 0 && reinterpret_cast<uintptr_t>(region_base(r)) % 16 == 0; }
+
 }  // namespace hb
 
 using namespace hb;
@@ -131,6 +402,28 @@ extern "C" int hb_pyr_down(const hb_pyr_down_desc *d, void *stream) {
     HB_REQUIRE(d->size == 3 || d->size == 5 || d->size == 7, HB_ERR_UNSUPPORTED, "hb_pyr_down: mask size %d unsupported (3,5,7); no CPU fallback", d->size);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = HB_OK;
+    if (!d->tmp.data && d->lap_fine.data && fine.width == 2 * coarse.width && fine.height == 2 * coarse.height) {
+        // exact-halving transition: blur + subsample + DoG in one kernel
+        hb_view lap = norm_view(d->lap_fine);
+        HB_REQUIRE(view_ok(lap) && lap.dtype == HB_F32 && lap.width == fine.width && lap.height == fine.height, HB_ERR_INVALID,
+                   "hb_pyr_down: lap_fine must be an f32 view of the fine level's size");
+        const PlaneRef f = plane_of(fine), c = plane_of(coarse), l = plane_of(lap);
+        if (vec_ok(f) && vec_ok(l) && c.stride % 2 == 0 && reinterpret_cast<uintptr_t>(region_base(c)) % 8 == 0) {
+            PyrFusedParams p;
+            memset(&p, 0, sizeof(p));
+            p.fine = region_base(f); p.coarse = region_base(c); p.lap = region_base(l);
+            p.fine_stride = f.stride; p.coarse_stride = c.stride; p.lap_stride = l.stride;
+            p.fw = f.w; p.fh = f.h; p.cw = c.w; p.ch = c.h;
+            for (int k = 0; k < d->size * d->size; ++k) p.coef[k] = d->coef_f32[k];
+            OpScope scope(s, "hb_pyr_down(fused blur+subsample+DoG)");
+            dim3 grid((p.fw + FD_TW - 1) / FD_TW, (p.fh + FD_TH - 1) / FD_TH);
+            if (d->size == 3) pyr_down_fused_kernel<3><<<grid, FD_NT, 0, s>>>(p);
+            else if (d->size == 5) pyr_down_fused_kernel<5><<<grid, FD_NT, 0, s>>>(p);
+            else pyr_down_fused_kernel<7><<<grid, FD_NT, 0, s>>>(p);
+            g_launches++;
+            return scope.finish();
+        }
+    }
     if (d->tmp.data) {
         // unfused form (tmp is part of the visible state): blur into tmp, then NN subsample
         hb_local_desc l;
@@ -179,8 +472,19 @@ extern "C" int hb_pyr_up(const hb_pyr_up_desc *d, void *stream) {
     HB_REQUIRE(view_ok(cg) && view_ok(cl) && view_ok(fg) && view_ok(fl), HB_ERR_INVALID, "hb_pyr_up: malformed view");
     HB_REQUIRE(cg.dtype == HB_F32 && cl.dtype == HB_F32 && fg.dtype == HB_F32 && fl.dtype == HB_F32, HB_ERR_UNSUPPORTED, "hb_pyr_up: f32 only; no CPU fallback");
     HB_REQUIRE(fg.width == fl.width && fg.height == fl.height, HB_ERR_INVALID, "hb_pyr_up: fine gaus / lap sizes differ");
-    PyrUpParams p{plane_of(cg), plane_of(cl), plane_of(fg), plane_of(fl)};
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const PlaneRef g = plane_of(cg), l = plane_of(cl), G = plane_of(fg), L = plane_of(fl);
+        if (G.w == 2 * g.w && G.h == 2 * g.h && L.w == 2 * l.w && L.h == 2 * l.h && g.w == l.w && g.h == l.h && vec_ok(G) && vec_ok(L)) {
+            PyrUpHalfParams q{region_base(g), region_base(l), region_base(G), region_base(L), g.stride, l.stride, G.stride, L.stride, G.w, G.h, g.w, g.h};
+            OpScope scope(s, "hb_pyr_up(exact halving)");
+            dim3 grid((G.w + 127) / 128, (G.h + 31) / 32);
+            pyr_up_half_kernel<<<grid, 256, 0, s>>>(q);
+            g_launches++;
+            return scope.finish();
+        }
+    }
+    PyrUpParams p{plane_of(cg), plane_of(cl), plane_of(fg), plane_of(fl)};
     OpScope scope(s, "hb_pyr_up");
     dim3 grid((fg.width + 31) / 32, (fg.height + 31) / 32);
     pyr_up_kernel<<<grid, dim3(32, 8), 0, s>>>(p);

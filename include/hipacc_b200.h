@@ -226,6 +226,33 @@ int hb_reduce_minmaxsum_f32(const hb_view *in, float result_host[3], void *strea
  * device memory ({float min, float max, double sum}, 16 bytes) for an NCCL all-reduce */
 int hb_reduce_minmaxsum_f32_async(const hb_view *in, void *partials_device, void *stream);
 
+/* ------------------------------------------------------------------ binning (histograms) */
+/*
+ * Kernel::binning() + binned_data(num_bins) (dsl/kernel.hpp:163-209): every pixel of the region
+ * contributes `bin(INDEX(pixel)) = VALUE(pixel)` and equal indices are combined with reduce() = +
+ * (the Histogram sample, samples-public/2_Global_Operators/Histogram/src/main.cpp:48-70).
+ * Replaces hipaccApplyBinningSegmented + the generated segmented-binning kernel
+ * (runtime/hipacc_cu.tpp:410-464, runtime/hipacc_cu_red.hpp:527-641).  Bins are uint32; indices
+ * >= num_bins are dropped like the emitted Put helper does (runtime/hipacc_cpu_red.hpp:71-76).
+ * hb_binning is blocking and writes num_bins values to host memory (the reference returns
+ * `new T[num_bins]`); the _async form leaves them in device memory (zeroed by the call) for an
+ * NCCL all-reduce across row strips.
+ */
+typedef enum {
+  HB_BIN_INDEX_SCALE = 0, /* idx = (uint)(pixel / p0 * num_bins), float arithmetic (Histogram sample: p0 = 255) */
+  HB_BIN_INDEX_PIXEL = 1  /* idx = (uint)pixel */
+} hb_bin_index;
+typedef enum { HB_BIN_VALUE_ONE = 0 /* count */, HB_BIN_VALUE_PIXEL = 1 /* (uint)pixel */ } hb_bin_value;
+typedef struct {
+  hb_view in;      /* HB_F32 or HB_U8 */
+  int num_bins;
+  int index_kind;  /* hb_bin_index */
+  int value_kind;  /* hb_bin_value */
+  double p0;
+} hb_binning_desc;
+int hb_binning(const hb_binning_desc *desc, uint32_t *bins_host, void *stream);
+int hb_binning_async(const hb_binning_desc *desc, uint32_t *bins_device, void *stream);
+
 /* ------------------------------------------------------------------ fused pipelines */
 /*
  * Harris corner detector, the 9-kernel pipeline of

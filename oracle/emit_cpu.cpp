@@ -422,4 +422,40 @@ int oc_reduce_minmaxsum_f32(const hb_view *v_, float out[3], double *sum_f64) {
     return HB_OK;
 }
 
+// -emit-cpu binning: BINNING_CPU_2D (runtime/hipacc_cpu_red.hpp:70-128): per-thread local bins over row
+// chunks, then a per-bin combine; the Put helper drops indices >= num_bins (:71-76).  bin(idx) = val with
+// reduce = + (Histogram/src/main.cpp:61-67).  C conversion float -> uint like g++/x86-64 (via a 64-bit
+// truncation, so negative indices wrap above num_bins and are dropped).
+int oc_binning(const hb_binning_desc *d, unsigned *bins) {
+    hb_view v = d->in; norm_view(v);
+    const int nb = d->num_bins, nthr = omp_get_max_threads();
+    std::vector<unsigned> lb((size_t)nthr * nb, 0u);
+    const float p0 = (float)d->p0;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < v.height; ++y) {
+        unsigned *my = lb.data() + (size_t)omp_get_thread_num() * nb;
+        for (int x = 0; x < v.width; ++x) {
+            unsigned idx, val;
+            if (v.dtype == HB_F32) {
+                const float e = static_cast<const float *>(v.data)[(size_t)(v.offset_y + y) * v.stride + v.offset_x + x];
+                idx = d->index_kind == HB_BIN_INDEX_SCALE ? (unsigned)(long long)(e / p0 * (float)(unsigned)nb) : (unsigned)(long long)e;
+                val = d->value_kind == HB_BIN_VALUE_ONE ? 1u : (unsigned)(long long)e;
+            } else if (v.dtype == HB_U8) {
+                const unsigned char e = static_cast<const unsigned char *>(v.data)[(size_t)(v.offset_y + y) * v.stride + v.offset_x + x];
+                idx = d->index_kind == HB_BIN_INDEX_SCALE ? (unsigned)(long long)((float)e / p0 * (float)(unsigned)nb) : (unsigned)e;
+                val = d->value_kind == HB_BIN_VALUE_ONE ? 1u : (unsigned)e;
+            } else {
+                continue;
+            }
+            if (idx < (unsigned)nb) my[idx] = my[idx] + val;
+        }
+    }
+    for (int i = 0; i < nb; ++i) {
+        unsigned a = 0;
+        for (int t = 0; t < nthr; ++t) a = a + lb[(size_t)t * nb + i];
+        bins[i] = a;
+    }
+    return (v.dtype == HB_F32 || v.dtype == HB_U8) ? HB_OK : HB_ERR_UNSUPPORTED;
+}
+
 }  // extern "C"

@@ -100,6 +100,11 @@ namespace smp_box {
 #undef WIDTH
 #undef HEIGHT
 #undef IMAGE
+namespace smp_hist {
+#include "2_Global_Operators/Histogram/src/main.cpp"
+}
+#undef WIDTH
+#undef HEIGHT
 #undef main
 
 // reference CPU runtime's reduction macro (runtime/hipacc_cpu_red.hpp:19-68)
@@ -658,6 +663,26 @@ int ref_sample_reduce_sum_f32(const float *in, int w, int h, float *result) {
     smp_redsum::Reduction k(is, acc);
     k.execute();
     *result = k.reduced_data();
+    return 0;
+}
+
+// sample Histogram kernel (Histogram/src/main.cpp:48-70): binning() + binned_data() executed by the DSL
+// (dsl/kernel.hpp:163-199); pixel values must stay below 255 (the DSL asserts on the bin index)
+int ref_sample_histogram_f32(const float *in, int w, int h, int num_bins, unsigned *bins) {
+    Image<float> I(w, h, const_cast<float *>(in));
+    Image<float> O(w, h);
+    Accessor<float> acc(I);
+    IterationSpace<float> is(O);
+    smp_hist::Histogram k(is, acc);
+    k.execute();
+    unsigned *b = k.binned_data(num_bins);
+    std::memcpy(bins, b, sizeof(unsigned) * num_bins);
+    delete[] b;
+    return 0;
+}
+// the sample's embedded plain-C checker (Histogram/src/main.cpp:122-127)
+int ref_sample_histogram_check(const float *in, unsigned *out, int w, int h, int num_bins) {
+    smp_hist::histogram(const_cast<float *>(in), out, w, h, num_bins);
     return 0;
 }
 

@@ -428,6 +428,21 @@ def test_full_size_c3_bilateral_windows(hb, oracle, dev):
         np.testing.assert_allclose(got[y0:y0 + 96, x0:x0 + 160], want[oy:oy + 96, ox:ox + 160], rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("h,w,depth,sz", [(200, 392, 3, 5), (264, 520, 4, 3), (96, 644, 3, 7), (130, 258, 2, 5)])
+def test_pyramid_exact_halving_multi_tile_vs_oracle(hb, oracle, dev, h, w, depth, sz):
+    """Even level sizes take the fused kernels (blur+subsample+DoG in one, Restore+Blend in one); several
+    128 x 32 tiles per level incl. partial tiles at the right / bottom edge."""
+    import torch
+    img = synth.image_np("float32", w, h, seed=60 + sz)
+    og, ol = oracle.pyramid(img, depth, M.GAUSS[sz])
+    pg = hb.Pyramid(to_dev(hb, img, dev), depth)
+    pl = hb.Pyramid(torch.zeros_like(pg.levels[0]), depth)
+    hb.pyramid_traverse(pg, pl, M.GAUSS[sz])
+    for lv in range(depth):
+        np.testing.assert_array_equal(to_np(pg.levels[lv]), og[lv])
+        np.testing.assert_array_equal(to_np(pl.levels[lv]), ol[lv])
+
+
 def test_full_size_c4_harris_strip_of_32k(hb, oracle, dev):
     """One 32768-wide strip (the per-GPU share at 8 GPUs is 32768 x 4096): fused kernel vs oracle pipeline."""
     img = synth.image_np("uint8", 32768, 512, seed=4)
