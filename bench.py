@@ -361,8 +361,11 @@ def extra_operators(hb, dev, peak):
     entry("C3_bilateral13x13_f32_8192", 8192 * 8192, 8 * 8192 * 8192, timeit(lambda: hb.bilateral(f, 13, cm, 16, A.MIRROR, dst=fo, stream=stream), reps=3, warm=1),
           "169 ex2 per pixel: MUFU/FP32-issue bound")
     part = torch.zeros(4, dtype=torch.float32, device=dev)
+    hbins = torch.zeros(256, dtype=torch.int32, device=dev)
     entry("C3_reduce_minmaxsum_f32_8192", 8192 * 8192, 4 * 8192 * 8192, timeit(lambda: hb.reduce_minmaxsum_async(fo, part, stream=stream)),
           "fused min+max+sum, one pass")
+    entry("hist256_f32_8192", 8192 * 8192, 4 * 8192 * 8192, timeit(lambda: hb.binning_async(f, hbins, stream=stream)),
+          "binning(): 256-bin histogram, per-warp shared-memory bins, one pass")
     # 1 read + 1 write references at the same size and timing method: what "HBM roofline" means in this loop
     c_src, c_dst = f, fo
     entry("ref_copy_torch_f32_8192", 8192 * 8192, 8 * 8192 * 8192, timeit(lambda: c_dst.copy_(c_src)), "torch copy_ (library kernel), measurement reference only")

@@ -44,6 +44,8 @@ def lib():
         L.hb_reduce.argtypes = [C.POINTER(A.hb_view), C.c_int, C.c_void_p, C.c_void_p]
         L.hb_reduce_minmaxsum_f32.argtypes = [C.POINTER(A.hb_view), C.POINTER(C.c_float), C.c_void_p]
         L.hb_reduce_minmaxsum_f32_async.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
+        L.hb_binning.argtypes = [C.POINTER(A.hb_binning_desc), C.c_void_p, C.c_void_p]
+        L.hb_binning_async.argtypes = [C.POINTER(A.hb_binning_desc), C.c_void_p, C.c_void_p]
         L.hb_harris.argtypes = [C.POINTER(A.hb_harris_desc), C.c_void_p]
         L.hb_pyr_down.argtypes = [C.POINTER(A.hb_pyr_down_desc), C.c_void_p]
         L.hb_pyr_up.argtypes = [C.POINTER(A.hb_pyr_up_desc), C.c_void_p]
@@ -186,6 +188,30 @@ def reduce(src, mode, roi=None, stream=None):
     res = np.zeros(1, dtype=A.DTYPE_NUMPY[v.dtype])
     _check(lib().hb_reduce(C.byref(v), mode, res.ctypes.data_as(C.c_void_p), stream_ptr(stream)), "hb_reduce")
     return res[0]
+
+
+def _binning_desc(src, num_bins, index_kind, value_kind, p0, roi):
+    d = A.hb_binning_desc()
+    d.in_ = view(src, roi)
+    d.num_bins, d.index_kind, d.value_kind, d.p0 = int(num_bins), index_kind, value_kind, float(p0)
+    return d
+
+
+def binning(src, num_bins, index_kind=A.BIN_INDEX_SCALE, value_kind=A.BIN_VALUE_ONE, p0=255.0, roi=None, stream=None):
+    """Kernel::binned_data(num_bins) for `bin(INDEX(pixel)) = VALUE(pixel)`, reduce = + (hb_binning, blocking)
+    -> numpy uint32[num_bins].  Defaults are the Histogram sample: bin(pixel/255.0f*num_bins) = 1."""
+    import numpy as np
+    d = _binning_desc(src, num_bins, index_kind, value_kind, p0, roi)
+    out = np.zeros(num_bins, dtype=np.uint32)
+    _check(lib().hb_binning(C.byref(d), out.ctypes.data_as(C.c_void_p), stream_ptr(stream)), "hb_binning")
+    return out
+
+
+def binning_async(src, bins, index_kind=A.BIN_INDEX_SCALE, value_kind=A.BIN_VALUE_ONE, p0=255.0, roi=None, stream=None):
+    """Same, bins left in the CUDA int32/uint32 tensor `bins` (zeroed by the call), no synchronisation."""
+    d = _binning_desc(src, bins.numel(), index_kind, value_kind, p0, roi)
+    _check(lib().hb_binning_async(C.byref(d), C.c_void_p(bins.data_ptr()), stream_ptr(stream)), "hb_binning_async")
+    return bins
 
 
 def harris(src, k=masks.HARRIS_K, threshold=masks.HARRIS_THRESHOLD, dst=None, roi=None, ghost=(0, 0), stream=None):

@@ -27,6 +27,9 @@ EPI_CAST, EPI_ADD_CAST, EPI_ADD_CLAMP_CAST, EPI_DIVI_CAST, EPI_DIVF_CAST = range
 # hb_point_kind
 (POINT_COPY, POINT_SQUARE, POINT_MUL, POINT_SUB, POINT_ADD, POINT_BLEND,
  POINT_SOBEL_COMBINE, POINT_HARRIS) = range(8)
+# hb_bin_index / hb_bin_value
+BIN_INDEX_SCALE, BIN_INDEX_PIXEL = 0, 1
+BIN_VALUE_ONE, BIN_VALUE_PIXEL = 0, 1
 
 
 class hb_view(C.Structure):
@@ -78,6 +81,10 @@ class hb_point_desc(C.Structure):
     ]
 
 
+class hb_binning_desc(C.Structure):
+    _fields_ = [("in_", hb_view), ("num_bins", C.c_int), ("index_kind", C.c_int), ("value_kind", C.c_int), ("p0", C.c_double)]
+
+
 class hb_harris_desc(C.Structure):
     _fields_ = [("in_", hb_view), ("out", hb_view), ("k", C.c_float), ("threshold", C.c_float)]
 
@@ -117,5 +124,6 @@ EXPORTS = [
     "hb_stream_synchronize",
     "hb_local_op", "hb_bilateral", "hb_point_op",
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
+    "hb_binning", "hb_binning_async",
     "hb_harris", "hb_pyr_down", "hb_pyr_up",
 ]

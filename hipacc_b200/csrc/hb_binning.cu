@@ -12,6 +12,7 @@
 #include "hb_common.cuh"
 #include "hb_internal.h"
 
+#include <cmath>
 #include <cstring>
 
 namespace hb {
@@ -22,7 +23,7 @@ struct BinParams {
     unsigned *bins;
     int num_bins, copies;  // copies of the bins in shared memory (0: global atomics only)
     int index_kind, value_kind;
-    float p0, nbf;
+    float p0, rp0, nbf;  // divisor, its refined reciprocal, (float)num_bins
 };
 
 constexpr int HT = 256, HU = 4;
@@ -41,17 +42,47 @@ __device__ __forceinline__ void unpack(const uint4 &v, uchar (&e)[16]) {
 // C `(uint)f` as g++ / x86-64 evaluates it: truncate through 64 bits, keep the low 32
 __device__ __forceinline__ unsigned f2u_c(float f) { return (unsigned)__float2ll_rz(f); }
 
+// a / b correctly rounded with the host-computed correctly rounded reciprocal r = RN(1/b): the FMA tail of
+// div.rn.f32's fast path without the MUFU.RCP; operands outside the guarded range (or r == 0) take __fdiv_rn.
+__device__ __forceinline__ float div_by_const(float a, float b, float r) {
+    const float aa = fabsf(a);
+    if (r != 0.0f && aa < 1e30f && (aa > 1e-30f || a == 0.0f)) {
+        const float q = __fmul_rn(a, r);
+        const float e = __fmaf_rn(-b, q, a);
+        return __fmaf_rn(e, r, q);
+    }
+    return __fdiv_rn(a, b);
+}
+
+// bin index of `v` = (uint)v under C semantics restricted to what can land in [0, num_bins): values in (-1, nb)
+// truncate toward zero (NaN converts to 0 on x86-64 and here), everything else is dropped (returns false).
+// Truncation without the conversion pipe: RZ-add of 2^23 leaves the integer part in the mantissa (nb <= 2^22).
+__device__ __forceinline__ bool f2bin(float v, float nbf, unsigned &idx) {
+    if (v >= nbf || v <= -1.0f) return false;
+    const float t = __fadd_rz(fmaxf(v, 0.0f), 8388608.0f);
+    idx = (unsigned)(__float_as_int(t) - 0x4B000000);
+    return true;
+}
+
 template <typename T>
 __device__ __forceinline__ void bin_put(const BinParams &p, unsigned *sh, T e) {
     unsigned idx, val;
+    bool ok;
     if (DtypeOf<T>::v == HB_F32) {
-        idx = p.index_kind == HB_BIN_INDEX_SCALE ? f2u_c(__fmul_rn(__fdiv_rn((float)e, p.p0), p.nbf)) : f2u_c((float)e);
-        val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : f2u_c((float)e);
+        const float f = (float)e;
+        const float v = p.index_kind == HB_BIN_INDEX_SCALE ? __fmul_rn(div_by_const(f, p.p0, p.rp0), p.nbf) : f;
+        ok = f2bin(v, p.nbf, idx);
+        val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : f2u_c(f);
     } else {
-        idx = p.index_kind == HB_BIN_INDEX_SCALE ? f2u_c(__fmul_rn(__fdiv_rn((float)e, p.p0), p.nbf)) : (unsigned)e;
+        if (p.index_kind == HB_BIN_INDEX_SCALE) {
+            ok = f2bin(__fmul_rn(div_by_const((float)e, p.p0, p.rp0), p.nbf), p.nbf, idx);
+        } else {
+            idx = (unsigned)e;
+            ok = idx < (unsigned)p.num_bins;
+        }
         val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : (unsigned)e;
     }
-    if (idx < (unsigned)p.num_bins) {
+    if (ok) {
         if (sh) atomicAdd(sh + idx, val);
         else atomicAdd(p.bins + idx, val);
     }
@@ -116,7 +147,7 @@ static BinScratch g_bin[16];
 static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStream_t s, const char *who) {
     hb_view v = norm_view(d->in);
     HB_REQUIRE(view_ok(v) && (v.dtype == HB_F32 || v.dtype == HB_U8), HB_ERR_UNSUPPORTED, "%s: needs a valid f32 or u8 view; no CPU fallback", who);
-    HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 24), HB_ERR_INVALID, "%s: num_bins %d out of range", who, d->num_bins);
+    HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 22), HB_ERR_INVALID, "%s: num_bins %d out of range", who, d->num_bins);
     HB_REQUIRE(d->index_kind == HB_BIN_INDEX_SCALE || d->index_kind == HB_BIN_INDEX_PIXEL, HB_ERR_INVALID, "%s: bad index kind", who);
     HB_REQUIRE(d->value_kind == HB_BIN_VALUE_ONE || d->value_kind == HB_BIN_VALUE_PIXEL, HB_ERR_INVALID, "%s: bad value kind", who);
     HB_REQUIRE(d->index_kind != HB_BIN_INDEX_SCALE || d->p0 != 0.0, HB_ERR_INVALID, "%s: p0 == 0", who);
@@ -125,6 +156,14 @@ static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStre
     p.in = v.data; p.stride = v.stride; p.w = v.width; p.h = v.height; p.ox = v.offset_x; p.oy = v.offset_y;
     p.bins = bins_dev; p.num_bins = d->num_bins; p.index_kind = d->index_kind; p.value_kind = d->value_kind;
     p.p0 = (float)d->p0; p.nbf = (float)(unsigned)d->num_bins;
+    {   // r = RN(1/p0): the correctly rounded reciprocal div_by_const() needs (Markstein: q' = RN(q + r*RN(a - b*q)) is
+        // the correctly rounded quotient for such an r unless b's mantissa is all ones); rp0 = 0 disables the fast path
+        const float b = p.p0;
+        unsigned bits;
+        memcpy(&bits, &b, sizeof(bits));
+        const bool plain = std::isfinite(b) && std::fabs(b) > 1e-30f && std::fabs(b) < 1e30f && (bits & 0x7FFFFFu) != 0x7FFFFFu;
+        p.rp0 = plain ? 1.0f / b : 0.0f;
+    }
     const int max_words = 48 * 1024 / 4;
     p.copies = d->num_bins > max_words ? 0 : (max_words / d->num_bins < HT / 32 ? max_words / d->num_bins : HT / 32);
     const size_t smem = (size_t)p.copies * d->num_bins * sizeof(unsigned);
@@ -156,7 +195,7 @@ extern "C" int hb_binning_async(const hb_binning_desc *d, uint32_t *bins_device,
 
 extern "C" int hb_binning(const hb_binning_desc *d, uint32_t *bins_host, void *stream) {
     HB_REQUIRE(d && bins_host, HB_ERR_INVALID, "hb_binning: null argument");
-    HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 24), HB_ERR_INVALID, "hb_binning: num_bins %d out of range", d->num_bins);
+    HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 22), HB_ERR_INVALID, "hb_binning: num_bins %d out of range", d->num_bins);
     int dev = 0;
     cudaGetDevice(&dev);
     BinScratch &sc = g_bin[dev & 15];

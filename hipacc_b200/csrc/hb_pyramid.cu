@@ -194,25 +194,46 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
     const int X0 = blockIdx.x * FD_TW, Y0 = blockIdx.y * FD_TH;
     const int CX0 = X0 >> 1, CY0 = Y0 >> 1;
 
-    // ---- stage the fine tile, CLAMP applied here (Gaussian's BoundaryCondition), so phase 1 is branch-free
+    // ---- stage the fine tile, CLAMP applied here (Gaussian's BoundaryCondition), so phase 1 is branch-free.
+    // Tiles whose staged columns lie inside the image (block-uniform test) take 16-byte loads with only the row
+    // index clamped; all loads of a thread are issued before the first shared-memory store.
     {
         constexpr int VPR = FD_FCOLS / 4;
+        constexpr int NV = FROWS * VPR, PER = (NV + FD_NT - 1) / FD_NT;
         const int xs = X0 - 4, ys = Y0 - 1 - H;
-        for (int v = tid; v < FROWS * VPR; v += FD_NT) {
-            const int r = v / VPR, c4 = v - r * VPR;
-            const int gy = min(max(ys + r, 0), p.fh - 1);
-            const int gx = xs + 4 * c4;
-            const float *row = p.fine + (size_t)gy * p.fine_stride;
-            float4 t;
-            if (gx >= 0 && gx + 3 < p.fw) {
-                t = __ldg(reinterpret_cast<const float4 *>(row + gx));
-            } else {
-                t.x = __ldg(row + min(max(gx, 0), p.fw - 1));
-                t.y = __ldg(row + min(max(gx + 1, 0), p.fw - 1));
-                t.z = __ldg(row + min(max(gx + 2, 0), p.fw - 1));
-                t.w = __ldg(row + min(max(gx + 3, 0), p.fw - 1));
+        if (xs >= 0 && xs + FD_FCOLS <= p.fw) {
+            float4 t[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int v = tid + k * FD_NT;
+                if (v < NV) {
+                    const int r = v / VPR, c4 = v - r * VPR;
+                    const int gy = min(max(ys + r, 0), p.fh - 1);
+                    t[k] = __ldg(reinterpret_cast<const float4 *>(p.fine + (size_t)gy * p.fine_stride + xs) + c4);
+                }
             }
-            *reinterpret_cast<float4 *>(ftile + r * FD_FCOLS + 4 * c4) = t;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int v = tid + k * FD_NT;
+                if (v < NV) reinterpret_cast<float4 *>(ftile)[v] = t[k];
+            }
+        } else {
+            for (int v = tid; v < NV; v += FD_NT) {
+                const int r = v / VPR, c4 = v - r * VPR;
+                const int gy = min(max(ys + r, 0), p.fh - 1);
+                const int gx = xs + 4 * c4;
+                const float *row = p.fine + (size_t)gy * p.fine_stride;
+                float4 t;
+                if (gx >= 0 && gx + 3 < p.fw) {
+                    t = __ldg(reinterpret_cast<const float4 *>(row + gx));
+                } else {
+                    t.x = __ldg(row + min(max(gx, 0), p.fw - 1));
+                    t.y = __ldg(row + min(max(gx + 1, 0), p.fw - 1));
+                    t.z = __ldg(row + min(max(gx + 2, 0), p.fw - 1));
+                    t.w = __ldg(row + min(max(gx + 3, 0), p.fw - 1));
+                }
+                reinterpret_cast<float4 *>(ftile)[v] = t;
+            }
         }
     }
     __syncthreads();

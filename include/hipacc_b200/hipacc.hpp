@@ -234,6 +234,15 @@ inline Epilogue add_clamp_cast(double a, double lo, double hi) { return {HB_EPI_
 inline Epilogue div_int_cast(int n) { return {HB_EPI_DIVI_CAST, {(double)n, 0, 0}}; }
 inline Epilogue div_float_cast(double n) { return {HB_EPI_DIVF_CAST, {n, 0, 0}}; }
 
+// the body of Kernel::binning(x, y, pixel):  bin(INDEX(pixel)) = VALUE(pixel)   (hb_bin_index / hb_bin_value)
+struct Binning {
+    int index_kind = -1, value_kind = HB_BIN_VALUE_ONE;
+    double p0 = 0.0;
+};
+inline Binning bin_scaled_count(double divisor) { return {HB_BIN_INDEX_SCALE, HB_BIN_VALUE_ONE, divisor}; }  // bin(pixel/divisor*num_bins) = 1
+inline Binning bin_pixel_count() { return {HB_BIN_INDEX_PIXEL, HB_BIN_VALUE_ONE, 0.0}; }                     // bin(pixel) = 1
+inline Binning bin_pixel_sum() { return {HB_BIN_INDEX_PIXEL, HB_BIN_VALUE_PIXEL, 0.0}; }                     // bin(pixel) = pixel
+
 struct Lowering {
     enum Kind { NONE, LOCAL, BILATERAL, POINT, HARRIS } kind = NONE;
     std::function<void(const hb_view &out, void *stream)> launch;
@@ -367,6 +376,8 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
     virtual void kernel() = 0;
     virtual b200::Lowering lower() { return {}; }
     virtual bin_t reduce(bin_t, bin_t) const { assert(false && "No reduce method specified"); return {}; }
+    virtual void binning(unsigned int, unsigned int, data_t) { assert(false && "No binning method specified"); }  // dsl/kernel.hpp:91
+    virtual b200::Binning lower_binning() { return {}; }
     void add_accessor(AccessorBase *acc) { inputs_.push_back(acc); }
 
     void execute(const HipaccExecutionParameterCuda &ep = nullptr) {
@@ -397,7 +408,23 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
         return reduction_result_;
     }
 
+    // binning over the OUTPUT image (dsl/kernel.hpp:163-199): returns `new bin_t[num_bins]`, owned by the caller
+    bin_t *binned_data(const unsigned int num_bins) {
+        if (!executed_) execute();
+        const b200::Binning b = lower_binning();
+        if (b.index_kind < 0 || probe_reduce_mode() != HB_REDUCE_SUM || sizeof(bin_t) != 4) {
+            std::fprintf(stderr, "ERROR: Kernel::binned_data(): needs lower_binning() and reduce() == left + right on 32-bit bins; "
+                                 "no device kernel otherwise, no host fallback\n");
+            return new bin_t[num_bins]();
+        }
+        num_bins_ = num_bins;
+        return hipaccApplyBinning<data_t, bin_t>(iteration_space_.rt(), num_bins, b.index_kind, b.value_kind, b.p0);
+    }
+
   protected:
+    unsigned int num_bins_ = 0;
+    unsigned int num_bins() const { return num_bins_; }
+    bin_t &bin(const unsigned int) { b200::host_body_called(); }
     // kernel()-body vocabulary; compiles, never runs on the host
     data_t &output() { b200::host_body_called(); }
     int x() const { b200::host_body_called(); }

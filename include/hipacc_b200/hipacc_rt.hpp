@@ -10,6 +10,7 @@
 //   hipaccLaunchKernel(kernelFn, grid, block, ep, t, smem, args...)   hipaccLaunchLocalOperator / hipaccLaunchPointOperator /
 //                                                                      hipaccLaunchBilateral / hipaccLaunchHarris (in, is, desc, ep, t)
 //   hipaccApplyReductionShared<T>(kernelFn, acc, threads, ppt, ep, tex, t)   hipaccApplyReduction<T>(acc, mode, ep, t)
+//   hipaccApplyBinningSegmented<T,T2,...>(kernelFn, acc, warps, units, bins, ep, tex, t)   hipaccApplyBinning<T>(acc, bins, index, value, p0, ep, t)
 //
 // Header-only; link with -lhipacc_b200.  No CUDA headers are needed by the including translation unit.
 #ifndef HIPACC_B200_RT_HPP
@@ -298,6 +299,22 @@ T hipaccApplyReduction(const HipaccAccessor<T> &acc, int reduce_mode, HipaccExec
 template <typename T>
 T hipaccApplyReduction(const HipaccImageCuda<T> &img, int reduce_mode, HipaccExecutionParameterCuda const &ep = nullptr, bool print_timing = false) {
     return hipaccApplyReduction<T>(HipaccAccessor<T>(img), reduce_mode, ep, print_timing);
+}
+// hipaccApplyBinningSegmented (hipacc_cu.tpp:410-464): blocking, returns `new T[num_bins]` owned by the caller.
+// The binning body is stated as (index kind, value kind, p0) -- hb_bin_index / hb_bin_value -- with reduce = +.
+template <typename T, typename BIN = uint>
+BIN *hipaccApplyBinning(const HipaccAccessor<T> &acc, unsigned num_bins, int index_kind, int value_kind, double p0,
+                        HipaccExecutionParameterCuda const &ep = nullptr, bool print_timing = false) {
+    static_assert(sizeof(BIN) == 4, "bins are 32-bit unsigned counters");
+    hipacc_b200::LaunchScope sc(ep, print_timing);
+    hb_binning_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.in = acc.view();
+    d.num_bins = (int)num_bins; d.index_kind = index_kind; d.value_kind = value_kind; d.p0 = p0;
+    BIN *bins = new BIN[num_bins]();
+    hipacc_b200::check(hb_binning(&d, reinterpret_cast<uint32_t *>(bins), sc.stream()), "hipaccApplyBinning()");
+    sc.done("binning", print_timing);
+    return bins;
 }
 // fused min + max + sum in one pass over HBM (float images)
 inline void hipaccApplyReductionMinMaxSum(const HipaccAccessor<float> &acc, float &mn, float &mx, float &sum,

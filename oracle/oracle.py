@@ -46,6 +46,7 @@ def emit_lib():
         _emit.oc_bilateral.argtypes = [C.POINTER(A.hb_bilateral_desc)]
         _emit.oc_point_op.argtypes = [C.POINTER(A.hb_point_desc)]
         _emit.oc_reduce_serial_f32.argtypes = [C.POINTER(A.hb_view), C.c_int, C.POINTER(C.c_float)]
+        _emit.oc_binning.argtypes = [C.POINTER(A.hb_binning_desc), C.POINTER(C.c_uint)]
         _emit.oc_reduce_minmaxsum_f32.argtypes = [C.POINTER(A.hb_view), C.POINTER(C.c_float), C.POINTER(C.c_double)]
     return _emit
 
@@ -149,6 +150,16 @@ def reduce_minmaxsum(img, roi=None):
     s = C.c_double()
     _check(emit_lib().oc_reduce_minmaxsum_f32(C.byref(v), o, C.byref(s)), "reduce_minmaxsum")
     return np.float32(o[0]), np.float32(o[1]), np.float32(o[2]), s.value
+
+
+def binning(img, num_bins, index_kind=A.BIN_INDEX_SCALE, value_kind=A.BIN_VALUE_ONE, p0=255.0, roi=None):
+    """-emit-cpu binning (BINNING_CPU_2D, runtime/hipacc_cpu_red.hpp:70-128) -> uint32[num_bins]"""
+    d = A.hb_binning_desc()
+    d.in_ = np_view(img, roi)
+    d.num_bins, d.index_kind, d.value_kind, d.p0 = int(num_bins), index_kind, value_kind, float(p0)
+    out = np.zeros(num_bins, dtype=np.uint32)
+    _check(emit_lib().oc_binning(C.byref(d), out.ctypes.data_as(C.POINTER(C.c_uint))), "binning")
+    return out
 
 
 def harris(img, k=M.HARRIS_K, threshold=M.HARRIS_THRESHOLD, return_intermediates=False):
@@ -323,6 +334,22 @@ def ref_global_reduce_f32(img, op, roi=None):
     _check(ref_lib().ref_global_reduce_f32(_p(img, C.c_float), img.shape[1], img.shape[0], op,
                                            _roi8(roi, None), C.byref(r)), "ref_global_reduce_f32")
     return np.float32(r.value)
+
+
+def ref_sample_histogram_f32(img, num_bins):
+    """the Histogram sample's Kernel (binning() + binned_data()) executed by the reference DSL"""
+    out = np.zeros(num_bins, dtype=np.uint32)
+    _check(ref_lib().ref_sample_histogram_f32(_p(img, C.c_float), img.shape[1], img.shape[0], int(num_bins),
+                                              out.ctypes.data_as(C.POINTER(C.c_uint))), "ref_sample_histogram_f32")
+    return out
+
+
+def ref_sample_histogram_check(img, num_bins):
+    """the sample's embedded plain-C histogram (Histogram/src/main.cpp:122-127)"""
+    out = np.zeros(num_bins, dtype=np.uint32)
+    _check(ref_lib().ref_sample_histogram_check(_p(img, C.c_float), out.ctypes.data_as(C.POINTER(C.c_uint)),
+                                                img.shape[1], img.shape[0], int(num_bins)), "ref_sample_histogram_check")
+    return out
 
 
 def ref_rt_reduce_f32(img, op):

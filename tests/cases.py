@@ -20,6 +20,8 @@ U8_SHAPE = (45, 70)
 F32_SHAPE = (39, 66)
 HARRIS_SHAPE = (96, 128)
 PYR_CASES = [(64, 96, 4, 5), (50, 77, 3, 3)]
+HIST_SHAPE = (61, 83)
+HIST_BINS = (256, 64, 1000)
 
 _golden = None
 

@@ -69,5 +69,21 @@ def main():
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(HERE, "reference_dsl.npz")), "bytes")
 
 
+HIST_SHAPE = (61, 83)
+HIST_BINS = (256, 64, 1000)
+
+
+def hist():
+    """reference_hist.npz: the Histogram sample's kernel (binning() + binned_data()) executed by the reference DSL."""
+    out = {}
+    img = synth.image_np("float32", HIST_SHAPE[1], HIST_SHAPE[0], seed=9, scale=254.99)
+    for nb in HIST_BINS:
+        out[f"hist_{nb}"] = O.ref_sample_histogram_f32(img, nb)
+    np.savez_compressed(os.path.join(HERE, "reference_hist.npz"), **out)
+    print("wrote", len(out), "arrays to reference_hist.npz")
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-hist" not in sys.argv:
+        main()
+    hist()

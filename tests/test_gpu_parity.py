@@ -320,6 +320,51 @@ def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
             np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
 
 
+# ------------------------------------------------------------------ binning / histogram
+@pytest.mark.parametrize("shape", [(61, 83), (300, 1031), (2, 5), (1, 1), (257, 4096)])
+@pytest.mark.parametrize("nb", [256, 64, 1000, 20000])
+def test_histogram_f32_vs_oracle(hb, oracle, dev, shape, nb):
+    img = synth.image_np("float32", shape[1], shape[0], seed=9, scale=254.99)
+    got = hb.binning(to_dev(hb, img, dev), nb)
+    np.testing.assert_array_equal(got, oracle.binning(img, nb))
+    assert int(got.sum()) == img.size
+
+
+def test_histogram_vs_golden(hb, dev):
+    import os
+    g = np.load(os.path.join(os.path.dirname(cases.GOLDEN_PATH), "reference_hist.npz"))
+    img = synth.image_np("float32", cases.HIST_SHAPE[1], cases.HIST_SHAPE[0], seed=9, scale=254.99)
+    for nb in cases.HIST_BINS:
+        np.testing.assert_array_equal(hb.binning(to_dev(hb, img, dev), nb), g[f"hist_{nb}"])
+
+
+def test_binning_kinds_roi_and_dropped_indices(hb, oracle, dev):
+    u8 = synth.image_np("uint8", 1000, 333, seed=12)
+    d = to_dev(hb, u8, dev)
+    for nb, vk in ((256, A.BIN_VALUE_ONE), (100, A.BIN_VALUE_ONE), (256, A.BIN_VALUE_PIXEL)):
+        np.testing.assert_array_equal(hb.binning(d, nb, A.BIN_INDEX_PIXEL, vk), oracle.binning(u8, nb, A.BIN_INDEX_PIXEL, vk))
+    roi = (701, 200, 13, 7)
+    np.testing.assert_array_equal(hb.binning(d, 256, A.BIN_INDEX_PIXEL, roi=roi), oracle.binning(u8, 256, A.BIN_INDEX_PIXEL, roi=roi))
+    f = synth.image_np("float32", 515, 129, seed=13, scale=300.0) - 20.0   # pixels < 0 and >= 255 are dropped
+    np.testing.assert_array_equal(hb.binning(to_dev(hb, f, dev), 256), oracle.binning(f, 256))
+    np.testing.assert_array_equal(hb.binning(to_dev(hb, f, dev), 256, roi=(300, 100, 5, 3)), oracle.binning(f, 256, roi=(300, 100, 5, 3)))
+    const = np.full((64, 512), 17.0, np.float32)   # every pixel in one bin: worst-case shared-memory contention
+    got = hb.binning(to_dev(hb, const, dev), 256)
+    assert got[17] == const.size and got.sum() == const.size
+
+
+def test_histogram_full_size_properties(hb, dev):
+    """8192^2 float (C3's image): counts sum to the pixel count and match torch.histc-free integer binning on the device"""
+    import torch
+    img = synth.image_torch("float32", 8192, 8192, seed=3, scale=254.99, device=dev)
+    got = hb.binning(img, 256)
+    assert int(got.sum()) == 8192 * 8192
+    # tensor / tensor is an IEEE division (tensor / python scalar multiplies by the reciprocal on CUDA)
+    idx = (img / torch.full_like(img, 255.0) * 256.0).to(torch.int64).flatten()
+    want = torch.bincount(idx, minlength=256).cpu().numpy().astype(np.uint32)
+    np.testing.assert_array_equal(got, want)
+
+
 # ------------------------------------------------------------------ pyramid
 @pytest.mark.parametrize("idx", range(len(cases.PYR_CASES)))
 @pytest.mark.parametrize("with_tmp", [False, True], ids=["fused_down", "unfused_down"])

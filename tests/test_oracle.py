@@ -84,6 +84,32 @@ def test_global_reduce_vs_golden(oracle):
     assert abs(s64 - f32.astype(np.float64).sum()) <= 1e-9 * abs(s64)
 
 
+def test_histogram_vs_golden(oracle):
+    """Histogram sample (binning() + binned_data()) executed by the reference DSL -> tests/golden/reference_hist.npz"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(cases.GOLDEN_PATH), "reference_hist.npz"))
+    img = synth.image_np("float32", cases.HIST_SHAPE[1], cases.HIST_SHAPE[0], seed=9, scale=254.99)
+    for nb in cases.HIST_BINS:
+        got = oracle.binning(img, nb)
+        np.testing.assert_array_equal(got, g[f"hist_{nb}"])
+        assert int(got.sum()) == img.size
+
+
+def test_binning_kinds_and_dropped_indices(oracle):
+    """indices >= num_bins are dropped (BINNING Put helper, runtime/hipacc_cpu_red.hpp:71-76); uchar pixel-indexed
+    histogram and value = pixel against numpy"""
+    u8 = synth.image_np("uint8", 97, 53, seed=12)
+    np.testing.assert_array_equal(oracle.binning(u8, 256, A.BIN_INDEX_PIXEL), np.bincount(u8.ravel(), minlength=256).astype(np.uint32))
+    np.testing.assert_array_equal(oracle.binning(u8, 100, A.BIN_INDEX_PIXEL), np.bincount(u8.ravel(), minlength=256)[:100].astype(np.uint32))
+    sums = np.bincount(u8.ravel(), weights=u8.ravel().astype(np.float64), minlength=256).astype(np.uint32)
+    np.testing.assert_array_equal(oracle.binning(u8, 256, A.BIN_INDEX_PIXEL, A.BIN_VALUE_PIXEL), sums)
+    f = synth.image_np("float32", 64, 40, seed=13, scale=300.0) - 20.0   # some pixels < 0 and >= 255: dropped
+    idx = (f / np.float32(255.0) * np.float32(256)).astype(np.int64)
+    want = np.bincount(idx[(idx >= 0) & (idx < 256) & (f > -1.0)], minlength=256).astype(np.uint32)
+    # (uint) of a value in (-1, 0) truncates to 0 in C
+    np.testing.assert_array_equal(oracle.binning(f, 256), want)
+
+
 # ------------------------------------------------------------------ (2) appendix A known-answer vectors
 @pytest.mark.parametrize("b", [A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT])
 def test_kat_sum3(oracle, b):
@@ -203,6 +229,14 @@ def test_reduce_modes_vs_reference(ref, mode):
         want = ref.ref_local_f32(f32, m, dom, mode, A.MIRROR)
         spec = S.domain_reduce_f32(m, A.MIRROR, mode) if dom else S.convolve_f32(m, A.MIRROR, mode)
         np.testing.assert_array_equal(ref.local_op(spec, f32), want)
+
+
+def test_histogram_vs_reference_and_sample_checker(ref):
+    img = synth.image_np("float32", 130, 77, seed=14, scale=254.99)
+    for nb in (256, 32):
+        want = ref.ref_sample_histogram_f32(img, nb)
+        np.testing.assert_array_equal(ref.binning(img, nb), want)
+        np.testing.assert_array_equal(ref.ref_sample_histogram_check(img, nb), want)
 
 
 def test_pyramid_char_sample_restores_input(ref):
