@@ -296,7 +296,10 @@ def main():
            "d2h_bytes_per_step": 4 * W * plan.rows * len(OPS) * world, "ms_per_step": float(t_e.item()) * 1e3,
            "api": "hb_image_write + 3 x hb_local_op + 3 x hb_image_read (pinned host buffers)"}
 
-    operators = extra_operators(hb, dev, peak) if (args.extra and world == 1) else None
+    if args.extra:
+        operators = extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream)
+    else:
+        operators = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -390,6 +393,72 @@ def extra_operators(hb, dev, peak):
     ms = timeit(lambda: hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream), reps=3, warm=1)
     n = 16384 * 16384
     entry("C5_pyramid8_f32_16384", n, int(23 * n * 4 / 3), ms, "fused down (blur+subsample, DoG) 9n + fused up 14n bytes per transition")
+    return res
+
+
+def extra_sharded(hb, dev, world, rank, stream):
+    """N > 1: the sharded BASELINE configs (strong scaling: the named global image cut into `world` row strips).
+    C4 Harris 32768^2 uchar (halo exchange + fused kernel per step), C5 pyramid 16384^2 float, 8 levels (one halo
+    exchange per level transition), C3 fused min/max/sum + one all-reduce per scalar.  Device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from hipacc_b200 import _abi as A, masks as M, strips, synth
+    res = {}
+
+    def timeit(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # C4: Harris on a 32768 x 32768 uchar image, `world` row strips with 2 ghost rows
+    Wc, Hc = 32768, 32768
+    plan = strips.StripPlan(Wc, Hc, world, rank, radius=2, boundary=A.CLAMP)
+    buf = torch.empty((plan.buffer_rows, Wc), dtype=torch.uint8, device=dev)
+    strips.owned(buf, plan).copy_(synth.image_torch("uint8", Wc, plan.rows, seed=4, y0=plan.y0, device=dev))
+    out = torch.empty_like(buf)
+
+    def harris_step():
+        strips.exchange_halos(buf, plan)
+        hb.harris(buf, dst=out, roi=plan.roi(), ghost=plan.ghost(), stream=stream)
+    ms = timeit(harris_step)
+    res["C4_harris_fused_u8_32768x32768_sharded"] = {"Gpx_s": Wc * Hc / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world,
+                                                      "note": f"strong scaling: {plan.rows} rows per rank + 2 ghost rows exchanged per step (NCCL send/recv)"}
+    del buf, out
+    # C5: 8-level pyramid of a 16384 x 16384 float image on row strips
+    Wp = Hp = 16384
+    pg = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev)
+    pl = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev)
+    pg.owned(0).copy_(synth.image_torch("float32", Wp, pg.plans[0].rows, seed=5, y0=pg.plans[0].y0, device=dev))
+    ms = timeit(lambda: strips.pyramid_traverse_strips(hb, pg, pl, M.GAUSS5, stream=stream), reps=3, warm=1)
+    res["C5_pyramid8_f32_16384_sharded"] = {"Gpx_s": Wp * Hp / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world,
+                                            "note": "strong scaling: 14 halo exchanges (4 rows per neighbour) + 14 fused level kernels per traversal"}
+    del pg, pl
+    # C3 reductions: per-rank fused min/max/sum partials + all-reduce (weak: 8192 x 8192 per rank)
+    f = hb.empty_image(A.F32, 8192, 8192, device=dev)
+    f.copy_(synth.image_torch("float32", 8192, 8192, seed=3, scale=255.0, y0=8192 * rank, device=dev))
+    part = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def reduce_step():
+        hb.reduce_minmaxsum_async(f, part, stream=stream)
+        mm = part[:2].clone()
+        sm = part[2:4].view(torch.float64).clone()
+        dist.all_reduce(mm[0:1], op=dist.ReduceOp.MIN)
+        dist.all_reduce(mm[1:2], op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    ms = timeit(reduce_step)
+    res["C3_reduce_minmaxsum_f32_8192_per_rank_allreduce"] = {"Gpx_s": 8192 * 8192 * world / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world,
+                                                              "note": "weak scaling: one pass over HBM per rank + 3 scalar all-reduces (NCCL)"}
     return res
 
 

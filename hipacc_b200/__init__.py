@@ -255,22 +255,28 @@ class Pyramid:
         assert base.dtype == torch.float32
 
 
+def _v(t):
+    """hb_view of a tensor, or of a (tensor, roi, ghost) triple (row-strip buffers)"""
+    return view(*t) if isinstance(t, tuple) else view(t)
+
+
 def pyr_down(fine, coarse, mask, lap_fine=None, tmp=None, stream=None):
+    """fine / coarse / lap_fine: 2-D CUDA tensors, or (tensor, roi, ghost) triples for row strips."""
     import numpy as np
     m = np.ascontiguousarray(mask, dtype=np.float32)
     d = A.hb_pyr_down_desc()
-    d.fine, d.coarse = view(fine), view(coarse)
+    d.fine, d.coarse = _v(fine), _v(coarse)
     if tmp is not None:
-        d.tmp = view(tmp)
+        d.tmp = _v(tmp)
     if lap_fine is not None:
-        d.lap_fine = view(lap_fine)
+        d.lap_fine = _v(lap_fine)
     d.size, d.coef_f32 = m.shape[0], m.ctypes.data_as(C.POINTER(C.c_float))
     _check(lib().hb_pyr_down(C.byref(d), stream_ptr(stream)), "hb_pyr_down")
 
 
 def pyr_up(coarse_gaus, coarse_lap, fine_gaus, fine_lap, stream=None):
     d = A.hb_pyr_up_desc()
-    d.coarse_gaus, d.coarse_lap, d.fine_gaus, d.fine_lap = view(coarse_gaus), view(coarse_lap), view(fine_gaus), view(fine_lap)
+    d.coarse_gaus, d.coarse_lap, d.fine_gaus, d.fine_lap = _v(coarse_gaus), _v(coarse_lap), _v(fine_gaus), _v(fine_lap)
     _check(lib().hb_pyr_up(C.byref(d), stream_ptr(stream)), "hb_pyr_up")
 
 

@@ -39,56 +39,53 @@ __device__ __forceinline__ void unpack(const uint4 &v, uchar (&e)[16]) {
     for (int i = 0; i < 16; ++i) e[i] = (uchar)(w[i >> 2] >> (8 * (i & 3)));
 }
 
-// C `(uint)f` as g++ / x86-64 evaluates it: truncate through 64 bits, keep the low 32
-__device__ __forceinline__ unsigned f2u_c(float f) { return (unsigned)__float2ll_rz(f); }
-
-// a / b correctly rounded with the host-computed correctly rounded reciprocal r = RN(1/b): the FMA tail of
-// div.rn.f32's fast path without the MUFU.RCP; operands outside the guarded range (or r == 0) take __fdiv_rn.
-__device__ __forceinline__ float div_by_const(float a, float b, float r) {
-    const float aa = fabsf(a);
-    if (r != 0.0f && aa < 1e30f && (aa > 1e-30f || a == 0.0f)) {
-        const float q = __fmul_rn(a, r);
-        const float e = __fmaf_rn(-b, q, a);
-        return __fmaf_rn(e, r, q);
-    }
-    return __fdiv_rn(a, b);
-}
-
-// bin index of `v` = (uint)v under C semantics restricted to what can land in [0, num_bins): values in (-1, nb)
-// truncate toward zero (NaN converts to 0 on x86-64 and here), everything else is dropped (returns false).
-// Truncation without the conversion pipe: RZ-add of 2^23 leaves the integer part in the mantissa (nb <= 2^22).
+// Bin index of the float value `v` = (uint)v.  The C conversion is defined for v in (-1, 2^32); the values that
+// truncate into [0, num_bins) are v in (-1, num_bins) -- everything else is dropped (the emitted Put helper drops
+// idx >= num_bins; v <= -1, +-inf and NaN are undefined in C: x86-64 wraps them to a huge index or to 0, the
+// reference's CUDA backend saturates -- this library drops them).  Branch-free: truncation is an RZ-add of 2^23
+// that leaves the integer part in the mantissa (num_bins <= 2^22), no conversion-pipe instruction.
 __device__ __forceinline__ bool f2bin(float v, float nbf, unsigned &idx) {
-    if (v >= nbf || v <= -1.0f) return false;
     const float t = __fadd_rz(fmaxf(v, 0.0f), 8388608.0f);
     idx = (unsigned)(__float_as_int(t) - 0x4B000000);
-    return true;
+    return v < nbf && v > -1.0f;   // false for NaN
 }
 
-template <typename T>
-__device__ __forceinline__ void bin_put(const BinParams &p, unsigned *sh, T e) {
-    unsigned idx, val;
-    bool ok;
-    if (DtypeOf<T>::v == HB_F32) {
-        const float f = (float)e;
-        const float v = p.index_kind == HB_BIN_INDEX_SCALE ? __fmul_rn(div_by_const(f, p.p0, p.rp0), p.nbf) : f;
-        ok = f2bin(v, p.nbf, idx);
-        val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : f2u_c(f);
+// pixel / p0 * num_bins, every operation correctly rounded.  FASTDIV: a / b through the host-computed correctly
+// rounded reciprocal r = RN(1/b): q = RN(a*r), e = RN(a - b*q) (exact), q' = RN(q + e*r) is the correctly rounded
+// quotient (Markstein; the host enables it only for finite b in [1e-15, 1e15] whose mantissa is not all ones) --
+// the FMA tail of div.rn.f32 without its MUFU.RCP.  |a| >= 1e30 cannot land in a bin (and could overflow the tail).
+template <bool FASTDIV>
+__device__ __forceinline__ bool scaled_index(const BinParams &p, float a, unsigned &idx) {
+    float q;
+    if (FASTDIV) {
+        const float q0 = __fmul_rn(a, p.rp0);
+        q = __fmaf_rn(__fmaf_rn(-p.p0, q0, a), p.rp0, q0);
     } else {
-        if (p.index_kind == HB_BIN_INDEX_SCALE) {
-            ok = f2bin(__fmul_rn(div_by_const((float)e, p.p0, p.rp0), p.nbf), p.nbf, idx);
-        } else {
-            idx = (unsigned)e;
-            ok = idx < (unsigned)p.num_bins;
-        }
-        val = p.value_kind == HB_BIN_VALUE_ONE ? 1u : (unsigned)e;
+        q = __fdiv_rn(a, p.p0);
     }
-    if (ok) {
-        if (sh) atomicAdd(sh + idx, val);
-        else atomicAdd(p.bins + idx, val);
-    }
+    const float v = fabsf(a) < 1e30f ? __fmul_rn(q, p.nbf) : -2.0f;
+    return f2bin(v, p.nbf, idx);
 }
 
-template <typename T>
+template <typename T, int INDEX, int VALUE, bool FASTDIV>
+__device__ __forceinline__ void bin_put(const BinParams &p, unsigned *sh, T e) {
+    unsigned idx;
+    bool ok;
+    if (INDEX == HB_BIN_INDEX_SCALE) {
+        ok = scaled_index<FASTDIV>(p, (float)e, idx);
+    } else if (DtypeOf<T>::v == HB_F32) {
+        ok = f2bin((float)e, p.nbf, idx);
+    } else {
+        idx = (unsigned)e;
+        ok = idx < (unsigned)p.num_bins;
+    }
+    // value = (uint)pixel: float pixels outside [0, 2^32) are undefined in C; they saturate here
+    const unsigned val = VALUE == HB_BIN_VALUE_ONE ? 1u : DtypeOf<T>::v == HB_F32 ? __float2uint_rz((float)e) : (unsigned)e;
+    unsigned *dst = (sh ? sh : p.bins) + idx;
+    if (ok) atomicAdd(dst, val);
+}
+
+template <typename T, int INDEX, int VALUE, bool FASTDIV>
 __global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ BinParams p) {
     typedef typename BinVec<T>::V V;
     constexpr int N = BinVec<T>::N;
@@ -121,11 +118,11 @@ __global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ Bin
                 T e[N];
                 unpack(v[k], e);
 #pragma unroll
-                for (int i = 0; i < N; ++i) bin_put<T>(p, my, e[i]);
+                for (int i = 0; i < N; ++i) bin_put<T, INDEX, VALUE, FASTDIV>(p, my, e[i]);
             }
         if (c == 0) {  // scalar head / tail pixels of this row
             const int nscal = head_n + (p.w - tail0);
-            for (int k = threadIdx.x; k < nscal; k += HT) bin_put<T>(p, my, row[k < head_n ? k : tail0 + (k - head_n)]);
+            for (int k = threadIdx.x; k < nscal; k += HT) bin_put<T, INDEX, VALUE, FASTDIV>(p, my, row[k < head_n ? k : tail0 + (k - head_n)]);
         }
     }
     if (p.copies) {
@@ -135,6 +132,22 @@ __global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ Bin
             for (int k = 0; k < p.copies; ++k) a += hsh[k * p.num_bins + i];
             if (a) atomicAdd(p.bins + i, a);
         }
+    }
+}
+
+template <typename T, int INDEX, int VALUE>
+static void launch_binning_kernel(const BinParams &p, bool fastdiv, int blocks, size_t smem, cudaStream_t s) {
+    if (INDEX == HB_BIN_INDEX_SCALE && fastdiv) binning_kernel<T, INDEX, VALUE, true><<<blocks, HT, smem, s>>>(p);
+    else binning_kernel<T, INDEX, VALUE, false><<<blocks, HT, smem, s>>>(p);
+}
+template <typename T>
+static void dispatch_binning(const BinParams &p, bool fastdiv, int blocks, size_t smem, cudaStream_t s) {
+    if (p.index_kind == HB_BIN_INDEX_SCALE) {
+        if (p.value_kind == HB_BIN_VALUE_ONE) launch_binning_kernel<T, HB_BIN_INDEX_SCALE, HB_BIN_VALUE_ONE>(p, fastdiv, blocks, smem, s);
+        else launch_binning_kernel<T, HB_BIN_INDEX_SCALE, HB_BIN_VALUE_PIXEL>(p, fastdiv, blocks, smem, s);
+    } else {
+        if (p.value_kind == HB_BIN_VALUE_ONE) launch_binning_kernel<T, HB_BIN_INDEX_PIXEL, HB_BIN_VALUE_ONE>(p, fastdiv, blocks, smem, s);
+        else launch_binning_kernel<T, HB_BIN_INDEX_PIXEL, HB_BIN_VALUE_PIXEL>(p, fastdiv, blocks, smem, s);
     }
 }
 
@@ -156,13 +169,13 @@ static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStre
     p.in = v.data; p.stride = v.stride; p.w = v.width; p.h = v.height; p.ox = v.offset_x; p.oy = v.offset_y;
     p.bins = bins_dev; p.num_bins = d->num_bins; p.index_kind = d->index_kind; p.value_kind = d->value_kind;
     p.p0 = (float)d->p0; p.nbf = (float)(unsigned)d->num_bins;
-    {   // r = RN(1/p0): the correctly rounded reciprocal div_by_const() needs (Markstein: q' = RN(q + r*RN(a - b*q)) is
-        // the correctly rounded quotient for such an r unless b's mantissa is all ones); rp0 = 0 disables the fast path
+    bool fastdiv = false;
+    if (d->index_kind == HB_BIN_INDEX_SCALE) {   // r = RN(1/p0), see scaled_index()
         const float b = p.p0;
         unsigned bits;
         memcpy(&bits, &b, sizeof(bits));
-        const bool plain = std::isfinite(b) && std::fabs(b) > 1e-30f && std::fabs(b) < 1e30f && (bits & 0x7FFFFFu) != 0x7FFFFFu;
-        p.rp0 = plain ? 1.0f / b : 0.0f;
+        fastdiv = std::isfinite(b) && std::fabs(b) >= 1e-15f && std::fabs(b) <= 1e15f && (bits & 0x7FFFFFu) != 0x7FFFFFu;
+        p.rp0 = fastdiv ? 1.0f / b : 0.0f;
     }
     const int max_words = 48 * 1024 / 4;
     p.copies = d->num_bins > max_words ? 0 : (max_words / d->num_bins < HT / 32 ? max_words / d->num_bins : HT / 32);
@@ -174,8 +187,8 @@ static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStre
     const int blocks = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
     int rc = check_cuda(cudaMemsetAsync(bins_dev, 0, sizeof(unsigned) * d->num_bins, s), "cudaMemsetAsync(bins)");
     if (rc) return rc;
-    if (v.dtype == HB_F32) binning_kernel<float><<<blocks, HT, smem, s>>>(p);
-    else binning_kernel<uchar><<<blocks, HT, smem, s>>>(p);
+    if (v.dtype == HB_F32) dispatch_binning<float>(p, fastdiv, blocks, smem, s);
+    else dispatch_binning<uchar>(p, fastdiv, blocks, smem, s);
     g_launches++;
     return HB_OK;
 }

@@ -72,7 +72,7 @@ struct Geo {
 template <int SX, int SY, typename MASK, int RPT, int BY, int NST>
 __global__ void __launch_bounds__(32 * BY) local_tma_f32_kernel(const __grid_constant__ LocalParams p,
                                                                 const __grid_constant__ CUtensorMap tmap, const int ntx,
-                                                                const int ntiles) {
+                                                                const int ntiles, const int stream_stores) {
     typedef Geo<SX, SY, RPT, BY, NST> G;
     constexpr int HX = G::HX, HY = G::HY, HXP = G::HXP, TH = G::TH, TWS = G::TWS, ROWS = G::ROWS;
     extern __shared__ unsigned char smem_raw[];
@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(32 * BY) local_tma_f32_kernel(const __grid_con
             if (gy >= p.is_h || gx >= p.is_w) continue;
             float *dst = out + (size_t)(p.out_oy + gy) * p.out_stride + p.out_ox + gx;
             if (vec_store && gx + 3 < p.is_w) {
-                *reinterpret_cast<float4 *>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                const float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                if (stream_stores) __stcs(reinterpret_cast<float4 *>(dst), o);   // written once, not re-read by this kernel
+                else *reinterpret_cast<float4 *>(dst) = o;
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -242,7 +244,12 @@ int launch_variant(const LocalParams &p, cudaStream_t s) {
     if (ntiles > 0x7fffffffLL) return HB_ERR_UNSUPPORTED;
     long long grid = (long long)sm_count() * ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
-    kern<<<(unsigned)grid, dim3(32, BY), G::SMEM_BYTES, s>>>(p, tmap, ntx, (int)ntiles);
+    static int stream_stores = -1;
+    if (stream_stores < 0) {
+        const char *e = getenv("HB_TMA_STCS");
+        stream_stores = e ? atoi(e) : 0;
+    }
+    kern<<<(unsigned)grid, dim3(32, BY), G::SMEM_BYTES, s>>>(p, tmap, ntx, (int)ntiles, stream_stores);
     g_launches++;
     return HB_OK;
 }

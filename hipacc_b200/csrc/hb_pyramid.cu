@@ -133,16 +133,19 @@ __global__ void __launch_bounds__(256) pyr_up_kernel(const __grid_constant__ Pyr
 // ((omx*omy)*p00 + (xf*omy)*p10) + (omx*yf)*p01) + (xf*yf)*p11.
 // ================================================================================================
 
-// generic (edge-safe) bilinear sample for the exact-halving case; `at(cx,cy)` returns the coarse value
+// generic (edge-safe) bilinear sample for the exact-halving case; `at(cx,cy)` returns the coarse value.
+// Row-strip sharding: `top_edge` says fine row 0 is the global top (x_mapped - 0.5 clamps at 0 only there; an
+// interior strip's row 0 blends with coarse row -1, a ghost row), `cy_max` is the last coarse row that exists
+// (ch - 1 at the global bottom, ch - 1 + ghost rows otherwise).
 template <typename F>
-__device__ __forceinline__ float lf_half(F at, int x, int y, int cw, int ch) {
+__device__ __forceinline__ float lf_half(F at, int x, int y, int cw, int cy_max, bool top_edge) {
     int x0, x1, y0, y1;
     float xf, yf;
     if (x & 1) { x0 = x >> 1; x1 = min(x0 + 1, cw - 1); xf = 0.25f; }
     else if (x == 0) { x0 = 0; x1 = min(1, cw - 1); xf = 0.0f; }
     else { x0 = (x >> 1) - 1; x1 = x0 + 1; xf = 0.75f; }
-    if (y & 1) { y0 = y >> 1; y1 = min(y0 + 1, ch - 1); yf = 0.25f; }
-    else if (y == 0) { y0 = 0; y1 = min(1, ch - 1); yf = 0.0f; }
+    if (y & 1) { y0 = y >> 1; y1 = min(y0 + 1, cy_max); yf = 0.25f; }
+    else if (y == 0 && top_edge) { y0 = 0; y1 = min(1, cy_max); yf = 0.0f; }
     else { y0 = (y >> 1) - 1; y1 = y0 + 1; yf = 0.75f; }
     const float omx = __fadd_rn(1.0f, -xf), omy = __fadd_rn(1.0f, -yf);
     float r = __fmul_rn(__fmul_rn(omx, omy), at(x0, y0));
@@ -176,6 +179,7 @@ struct PyrFusedParams {
     float *coarse, *lap;
     int fine_stride, coarse_stride, lap_stride;
     int fw, fh, cw, ch;
+    int fgt, fgb;   // ghost rows of real neighbour data above / below the fine region (row-strip sharding)
     float coef[49];
 };
 
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
                 const int v = tid + k * FD_NT;
                 if (v < NV) {
                     const int r = v / VPR, c4 = v - r * VPR;
-                    const int gy = min(max(ys + r, 0), p.fh - 1);
+                    const int gy = min(max(ys + r, -p.fgt), p.fh - 1 + p.fgb);
                     t[k] = __ldg(reinterpret_cast<const float4 *>(p.fine + (size_t)gy * p.fine_stride + xs) + c4);
                 }
             }
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
         } else {
             for (int v = tid; v < NV; v += FD_NT) {
                 const int r = v / VPR, c4 = v - r * VPR;
-                const int gy = min(max(ys + r, 0), p.fh - 1);
+                const int gy = min(max(ys + r, -p.fgt), p.fh - 1 + p.fgb);
                 const int gx = xs + 4 * c4;
                 const float *row = p.fine + (size_t)gy * p.fine_stride;
                 float4 t;
@@ -284,7 +288,9 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
     const int tx = tid & 31, ty = tid >> 5;
     const int x = X0 + 4 * tx, y = Y0 + 4 * ty;
     if (x >= p.fw || y >= p.fh) return;
-    const bool edge = X0 == 0 || Y0 == 0 || X0 + FD_TW >= p.fw || Y0 + FD_TH >= p.fh;
+    // interior strips (ghost rows present) have no vertical edge: their halo coarse rows -1 / ch were computed
+    // in phase 1 from the ghost rows
+    const bool edge = X0 == 0 || (Y0 == 0 && p.fgt == 0) || X0 + FD_TW >= p.fw || (Y0 + FD_TH >= p.fh && (p.fgb == 0 || Y0 + FD_TH > p.fh));
     float o[4][4];
     if (!edge) {
         float c[4][4];
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
             for (int i = 0; i < 4; ++i) {
                 const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
                 const float f = ftile[(yy - Y0 + 1 + H) * FD_FCOLS + 4 + (xx - X0)];
-                o[j][i] = __fadd_rn(f, -lf_half(at, xx, yy, p.cw, p.ch));
+                o[j][i] = __fadd_rn(f, -lf_half(at, xx, yy, p.cw, p.ch - 1 + (p.fgb > 0 ? 1 : 0), p.fgt == 0));
             }
     }
 #pragma unroll
@@ -332,6 +338,7 @@ struct PyrUpHalfParams {
     float *fg, *fl;
     int cg_stride, cl_stride, fg_stride, fl_stride;
     int fw, fh, cw, ch;
+    int cgt, cgb;   // ghost rows of the coarse planes (row-strip sharding; filled by the halo exchange)
 };
 
 // Restore + Blend for the exact-halving case: 4 x 4 fine block per thread, the two 4 x 4 coarse neighbourhoods
@@ -355,7 +362,8 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i) l[j][i] = p.fl[(size_t)min(y + j, p.fh - 1) * p.fl_stride + min(x + i, p.fw - 1)];
     }
-    if (full && x > 0 && y > 0) {
+    const int cy_max = p.ch - 1 + p.cgb;
+    if (full && x > 0 && (y > 0 || p.cgt > 0)) {
         const int m = x >> 1, k = y >> 1;
         float g[4][4], c[4][4];
         const int c0 = m - 1, c3 = min(m + 2, p.cw - 1), c2 = min(m + 1, p.cw - 1);  // m even: (m, m+1) is an 8-byte aligned pair
@@ -363,8 +371,8 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
                           ((reinterpret_cast<uintptr_t>(p.cg) | reinterpret_cast<uintptr_t>(p.cl)) % 8 == 0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int cy = min(k - 1 + j, p.ch - 1);
-            const float *rg = p.cg + (size_t)cy * p.cg_stride, *rl = p.cl + (size_t)cy * p.cl_stride;
+            const int cy = min(k - 1 + j, cy_max);   // >= cy_min: y == 0 takes this path only with ghost rows
+            const float *rg = p.cg + (ptrdiff_t)cy * p.cg_stride, *rl = p.cl + (ptrdiff_t)cy * p.cl_stride;
             g[j][0] = __ldg(rg + c0); c[j][0] = __ldg(rl + c0);
             if (pair) {
                 const float2 a = __ldg(reinterpret_cast<const float2 *>(rg + m)), b = __ldg(reinterpret_cast<const float2 *>(rl + m));
@@ -382,15 +390,15 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
                 ol[j][i] = __fadd_rn(lf_block(c, i, j), __fdiv_rn(l[j][i], 2.0f));
             }
     } else {
-        auto atg = [&](int cx, int cy) { return __ldg(p.cg + (size_t)cy * p.cg_stride + cx); };
-        auto atl = [&](int cx, int cy) { return __ldg(p.cl + (size_t)cy * p.cl_stride + cx); };
+        auto atg = [&](int cx, int cy) { return __ldg(p.cg + (ptrdiff_t)cy * p.cg_stride + cx); };
+        auto atl = [&](int cx, int cy) { return __ldg(p.cl + (ptrdiff_t)cy * p.cl_stride + cx); };
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
-                og[j][i] = __fadd_rn(lf_half(atg, xx, yy, p.cw, p.ch), l[j][i]);
-                ol[j][i] = __fadd_rn(lf_half(atl, xx, yy, p.cw, p.ch), __fdiv_rn(l[j][i], 2.0f));
+                og[j][i] = __fadd_rn(lf_half(atg, xx, yy, p.cw, cy_max, p.cgt == 0), l[j][i]);
+                ol[j][i] = __fadd_rn(lf_half(atl, xx, yy, p.cw, cy_max, p.cgt == 0), __fdiv_rn(l[j][i], 2.0f));
             }
     }
 #pragma unroll
@@ -435,6 +443,11 @@ extern "C" int hb_pyr_down(const hb_pyr_down_desc *d, void *stream) {
             p.fine = region_base(f); p.coarse = region_base(c); p.lap = region_base(l);
             p.fine_stride = f.stride; p.coarse_stride = c.stride; p.lap_stride = l.stride;
             p.fw = f.w; p.fh = f.h; p.cw = c.w; p.ch = c.h;
+            // ghost rows (row-strip sharding): the coarse halo row above needs fine rows down to -(H+1), the one
+            // below up to fh + H + 1; fewer ghost rows than that cannot reproduce the unsharded result
+            p.fgt = fine.ghost_top; p.fgb = fine.ghost_bottom;
+            HB_REQUIRE((p.fgt == 0 || p.fgt >= d->size / 2 + 1) && (p.fgb == 0 || p.fgb >= d->size / 2 + 2), HB_ERR_INVALID,
+                       "hb_pyr_down: a sharded fine level needs >= %d ghost rows above and >= %d below", d->size / 2 + 1, d->size / 2 + 2);
             for (int k = 0; k < d->size * d->size; ++k) p.coef[k] = d->coef_f32[k];
             OpScope scope(s, "hb_pyr_down(fused blur+subsample+DoG)");
             dim3 grid((p.fw + FD_TW - 1) / FD_TW, (p.fh + FD_TH - 1) / FD_TH);
@@ -445,6 +458,8 @@ extern "C" int hb_pyr_down(const hb_pyr_down_desc *d, void *stream) {
             return scope.finish();
         }
     }
+    HB_REQUIRE(fine.ghost_top == 0 && fine.ghost_bottom == 0, HB_ERR_UNSUPPORTED,
+               "hb_pyr_down: ghost rows (row-strip sharding) need the fused exact-halving path (even level sizes, 16-byte aligned rows, no tmp)");
     if (d->tmp.data) {
         // unfused form (tmp is part of the visible state): blur into tmp, then NN subsample
         hb_local_desc l;
@@ -497,7 +512,9 @@ extern "C" int hb_pyr_up(const hb_pyr_up_desc *d, void *stream) {
     {
         const PlaneRef g = plane_of(cg), l = plane_of(cl), G = plane_of(fg), L = plane_of(fl);
         if (G.w == 2 * g.w && G.h == 2 * g.h && L.w == 2 * l.w && L.h == 2 * l.h && g.w == l.w && g.h == l.h && vec_ok(G) && vec_ok(L)) {
-            PyrUpHalfParams q{region_base(g), region_base(l), region_base(G), region_base(L), g.stride, l.stride, G.stride, L.stride, G.w, G.h, g.w, g.h};
+            HB_REQUIRE(cg.ghost_top == cl.ghost_top && cg.ghost_bottom == cl.ghost_bottom, HB_ERR_INVALID, "hb_pyr_up: coarse gaus / lap ghost rows differ");
+            PyrUpHalfParams q{region_base(g), region_base(l), region_base(G), region_base(L), g.stride, l.stride, G.stride, L.stride, G.w, G.h, g.w, g.h,
+                              cg.ghost_top, cg.ghost_bottom};
             OpScope scope(s, "hb_pyr_up(exact halving)");
             dim3 grid((G.w + 127) / 128, (G.h + 31) / 32);
             pyr_up_half_kernel<<<grid, 256, 0, s>>>(q);
@@ -505,6 +522,8 @@ extern "C" int hb_pyr_up(const hb_pyr_up_desc *d, void *stream) {
             return scope.finish();
         }
     }
+    HB_REQUIRE(cg.ghost_top == 0 && cg.ghost_bottom == 0 && cl.ghost_top == 0 && cl.ghost_bottom == 0, HB_ERR_UNSUPPORTED,
+               "hb_pyr_up: ghost rows (row-strip sharding) need the exact-halving path (even level sizes, 16-byte aligned rows)");
     PyrUpParams p{plane_of(cg), plane_of(cl), plane_of(fg), plane_of(fl)};
     OpScope scope(s, "hb_pyr_up");
     dim3 grid((fg.width + 31) / 32, (fg.height + 31) / 32);

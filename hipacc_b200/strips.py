@@ -118,3 +118,80 @@ def allreduce_minmaxsum(mn, mx, sm, group=None, device=None):
         dist.all_reduce(t_mx, op=dist.ReduceOp.MAX, group=group)
         dist.all_reduce(t_sm, op=dist.ReduceOp.SUM, group=group)
     return float(t_mn.item()), float(t_mx.item()), float(t_sm.item())
+
+
+# ----------------------------------------------------------------------------- sharded pyramids
+class StripPyramid:
+    """This rank's row strips of every level of an image pyramid (level l = (width >> l) x (height >> l)).
+
+    Every level is cut at the same relative rows (rank * H_l / world), which requires the strip boundaries of level
+    0 to be multiples of 2^(depth-1): then a strip's local row parity equals the global one and the NN / LF
+    mappings of the level transitions are unchanged.  Each level buffer carries `radius` ghost rows per interior
+    side: the fused down kernel needs mask/2 + 2 rows of the finer level, the up kernel one row of the coarser."""
+
+    def __init__(self, width, height, depth, world, rank, radius, device, stride_align=64):
+        import torch
+        assert height % (world << (depth - 1)) == 0 and width % (1 << (depth - 1)) == 0, \
+            "sharded pyramid: level-0 strips must be multiples of 2^(depth-1) rows and the width of 2^(depth-1)"
+        self.depth, self.world, self.rank = depth, world, rank
+        self.plans = [StripPlan(width >> l, height >> l, world, rank, radius, A.CLAMP) for l in range(depth)]
+        for p in self.plans:
+            p.validate()
+        self.bufs = []
+        for p in self.plans:
+            stride = (p.width + stride_align - 1) // stride_align * stride_align
+            self.bufs.append(torch.zeros((p.buffer_rows, stride), dtype=torch.float32, device=device))
+
+    def owned(self, l):
+        return owned(self.bufs[l], self.plans[l])[:, :self.plans[l].width]
+
+    def strip(self, l):
+        """(tensor, roi, ghost) of level l: the owned rows with their ghost rows declared"""
+        p = self.plans[l]
+        return (self.bufs[l][:, :p.width], p.roi(), p.ghost())
+
+    def region(self, l):
+        """(tensor, roi, no ghosts): the owned rows only (outputs)"""
+        p = self.plans[l]
+        return (self.bufs[l][:, :p.width], p.roi(), (0, 0))
+
+
+def exchange_many(pairs, group=None):
+    """One batched halo exchange for several (buffer, plan) pairs (a single NCCL group launch)."""
+    import torch.distributed as dist
+    ops = []
+    for buf, plan in pairs:
+        if plan.world == 1 or plan.radius == 0:
+            continue
+        R, gt, rows = plan.radius, plan.ghost_top, plan.rows
+        if plan._has_up():
+            ops.append(dist.P2POp(dist.isend, buf[gt:gt + R], plan.up(), group))
+            ops.append(dist.P2POp(dist.irecv, buf[0:gt], plan.up(), group))
+        if plan._has_down():
+            ops.append(dist.P2POp(dist.isend, buf[gt + rows - R:gt + rows], plan.down(), group))
+            ops.append(dist.P2POp(dist.irecv, buf[gt + rows:gt + rows + plan.ghost_bottom], plan.down(), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def pyramid_down_step(hb, pg, pl, l, mask, stream=None):
+    """level l-1 -> l on this rank's strips (ghost rows of gaus(l-1) must be current)"""
+    hb.pyr_down(pg.strip(l - 1), pg.region(l), mask, lap_fine=pl.region(l - 1), stream=stream)
+
+
+def pyramid_up_step(hb, pg, pl, l, stream=None):
+    """level l+1 -> l on this rank's strips (ghost rows of gaus(l+1) and lap(l+1) must be current)"""
+    hb.pyr_up(pg.strip(l + 1), pl.strip(l + 1), pg.region(l), pl.region(l), stream=stream)
+
+
+def pyramid_traverse_strips(hb, pg, pl, mask, stream=None, group=None, exchange=exchange_many):
+    """The Gaussian / Laplacian pyramid traversal (Gaussian_Laplacian_Pyramid/src/main.cpp:199-248) on row strips:
+    one halo exchange (radius rows to each neighbour) before every level transition, kernels unchanged otherwise;
+    results are bit-identical to the unsharded traversal."""
+    for l in range(1, pg.depth):
+        exchange([(pg.bufs[l - 1], pg.plans[l - 1])], group)
+        pyramid_down_step(hb, pg, pl, l, mask, stream)
+    for l in range(pg.depth - 2, -1, -1):
+        exchange([(pg.bufs[l + 1], pg.plans[l + 1]), (pl.bufs[l + 1], pl.plans[l + 1])], group)
+        pyramid_up_step(hb, pg, pl, l, stream)

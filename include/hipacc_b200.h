@@ -234,6 +234,9 @@ int hb_reduce_minmaxsum_f32_async(const hb_view *in, void *partials_device, void
  * Replaces hipaccApplyBinningSegmented + the generated segmented-binning kernel
  * (runtime/hipacc_cu.tpp:410-464, runtime/hipacc_cu_red.hpp:527-641).  Bins are uint32; indices
  * >= num_bins are dropped like the emitted Put helper does (runtime/hipacc_cpu_red.hpp:71-76).
+ * A float index value v is defined (C conversion rules) for v > -1; v <= -1, +-inf and NaN are
+ * undefined in C (x86-64 wraps them to a huge index or 0, the reference's CUDA backend
+ * saturates) and are dropped here.  num_bins <= 2^22.
  * hb_binning is blocking and writes num_bins values to host memory (the reference returns
  * `new T[num_bins]`); the _async form leaves them in device memory (zeroed by the call) for an
  * NCCL all-reduce across row strips.

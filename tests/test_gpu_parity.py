@@ -488,6 +488,53 @@ def test_pyramid_exact_halving_multi_tile_vs_oracle(hb, oracle, dev, h, w, depth
         np.testing.assert_array_equal(to_np(pl.levels[lv]), ol[lv])
 
 
+@pytest.mark.parametrize("world,h,w,depth,sz", [(2, 256, 392, 3, 5), (4, 512, 264, 4, 3), (3, 384, 520, 3, 7), (8, 1024, 256, 4, 5)])
+def test_pyramid_row_strips_equal_unsharded(hb, dev, world, h, w, depth, sz):
+    """SURVEY 8e pyramid sharding: every rank's strips (ghost rows filled by the halo exchange, emulated here by
+    device copies between the strip buffers of all ranks in one process) give bit-identical levels."""
+    import torch
+    from hipacc_b200 import strips
+    img = to_dev(hb, synth.image_np("float32", w, h, seed=70 + world), dev)
+    pg = hb.Pyramid(img.clone(), depth)
+    pl = hb.Pyramid(torch.zeros_like(img), depth)
+    hb.pyramid_traverse(pg, pl, M.GAUSS[sz])
+
+    R = sz // 2 + 2
+    pgs = [strips.StripPyramid(w, h, depth, world, r, R, dev) for r in range(world)]
+    pls = [strips.StripPyramid(w, h, depth, world, r, R, dev) for r in range(world)]
+    for r in range(world):
+        p0 = pgs[r].plans[0]
+        pgs[r].owned(0).copy_(img[p0.y0:p0.y1])
+        for l in range(depth):   # poison the ghost rows: stale data must never be read
+            pgs[r].bufs[l][:pgs[r].plans[l].ghost_top] = float("nan")
+            pls[r].bufs[l][:pls[r].plans[l].ghost_top] = float("nan")
+
+    def exchange_all(pyrs, l):
+        for r in range(world):
+            pl_, buf = pyrs[r].plans[l], pyrs[r].bufs[l]
+            if pl_.ghost_top:
+                q, src = pyrs[r - 1].plans[l], pyrs[r - 1].bufs[l]
+                buf[0:pl_.ghost_top] = src[q.ghost_top + q.rows - R:q.ghost_top + q.rows]
+            if pl_.ghost_bottom:
+                q, src = pyrs[r + 1].plans[l], pyrs[r + 1].bufs[l]
+                buf[pl_.ghost_top + pl_.rows:pl_.ghost_top + pl_.rows + R] = src[q.ghost_top:q.ghost_top + R]
+
+    for l in range(1, depth):
+        exchange_all(pgs, l - 1)
+        for r in range(world):
+            strips.pyramid_down_step(hb, pgs[r], pls[r], l, M.GAUSS[sz])
+    for l in range(depth - 2, -1, -1):
+        exchange_all(pgs, l + 1)
+        exchange_all(pls, l + 1)
+        for r in range(world):
+            strips.pyramid_up_step(hb, pgs[r], pls[r], l)
+    for l in range(depth):
+        got_g = torch.cat([pgs[r].owned(l) for r in range(world)])
+        got_l = torch.cat([pls[r].owned(l) for r in range(world)])
+        np.testing.assert_array_equal(to_np(got_g), to_np(pg.levels[l]))
+        np.testing.assert_array_equal(to_np(got_l), to_np(pl.levels[l]))
+
+
 def test_full_size_c4_harris_strip_of_32k(hb, oracle, dev):
     """One 32768-wide strip (the per-GPU share at 8 GPUs is 32768 x 4096): fused kernel vs oracle pipeline."""
     img = synth.image_np("uint8", 32768, 512, seed=4)

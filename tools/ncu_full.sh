@@ -7,7 +7,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 IFS='|' read -ra KS <<< "$RE"
 for k in "${KS[@]}"; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 3 -c 1 -f -o $OUT/full_$k \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$k" -s ${NCU_SKIP:-3} -c 1 -f -o $OUT/full_$k \
       python bench.py --steps 1 --warmup 3 --extra --no-cpu --no-e2e --no-graph > $OUT/ncu_$k.log 2>&1
   ncu -i $OUT/full_$k.ncu-rep --page raw --csv > $OUT/full_$k.raw.csv 2>/dev/null
   python tools/ncu_keys.py $OUT/full_$k.raw.csv > $OUT/full_$k.txt 2>&1
