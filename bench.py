@@ -104,6 +104,7 @@ def cpu_baseline(rows, repeats=3):
     import numpy as np
     from hipacc_b200 import synth
     from oracle import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     img = synth.image_np("float32", W, rows, seed=2)
     specs = specs_for_workload()
     outs = [np.empty_like(img) for _ in specs]
@@ -126,6 +127,7 @@ def run_reference(args):
     import numpy as np
     from hipacc_b200 import synth
     from oracle import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     rows = 4096   # bounded sample: half of the image per step
     img = synth.image_np("float32", W, rows, seed=2)
     specs = specs_for_workload()
@@ -163,6 +165,7 @@ def main():
     ap.add_argument("--extra", action="store_true", help="also time the other BASELINE configs (C1, C3, C4 strip, C5) into 'operators'")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning sweeps only)")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo exchange by peer-to-peer push kernel (default) or NCCL send/recv")
     ap.add_argument("--no-graph", action="store_true", help="launch every operator from the host instead of replaying a CUDA graph of one step")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -189,7 +192,7 @@ def main():
     plan = strips.StripPlan(W, H * world, world, rank, radius=1, boundary=A.MIRROR)
     plan.validate()
     stride = (W + 63) // 64 * 64
-    buf = torch.empty((plan.buffer_rows, stride), dtype=torch.float32, device=dev)
+    buf = hb.alloc_image(A.F32, stride, plan.buffer_rows, device=dev)   # a whole CUDA allocation: exportable through CUDA IPC
     strips.owned(buf, plan)[:, :W] = synth.image_torch("float32", W, plan.rows, seed=2, y0=plan.y0, device=dev)
     src = buf[:, :W]
     outs = [hb.empty_image(A.F32, W, plan.buffer_rows, device=dev) for _ in OPS]
@@ -198,27 +201,45 @@ def main():
     stream = torch.cuda.Stream(device=dev)       # the stream every kernel of the timed region runs on
     torch.cuda.set_stream(stream)
 
+    halo = strips.P2PHalo(hb, buf, plan) if (world > 1 and args.halo == "p2p") else None
+
+    skip_exchange = bool(int(os.environ.get("HB_BENCH_NO_EXCHANGE", "0")))   # diagnosis only: kernels without the halo exchange
+
     def step_direct():
-        strips.exchange_halos(buf, plan)            # ghost rows from the neighbours (no-op at N = 1)
+        if skip_exchange:
+            pass
+        elif halo is not None:
+            halo.exchange(stream)                   # one kernel: push edge rows into the neighbours' ghost rows over NVLink
+        else:
+            strips.exchange_halos(buf, plan)        # NCCL send/recv (no-op at N = 1)
         for s, o in zip(specs, outs):
             hb.local_op(s, src, dst=o, roi_in=roi, roi_out=roi, ghost=ghost, stream=stream)
 
-    # One step = three operator launches.  At N = 1 the step is captured once into a CUDA graph and replayed
-    # (the reference's own -use-graph mode, runtime/hipacc_cu_standalone.hpp:331-356), so the timed region is
-    # not bounded by the Python host; N > 1 keeps direct launches because the NCCL halo exchange is part of it.
-    use_graph = world == 1 and not args.no_graph
-    launches_per_step = len(OPS)
+    # One step = (halo exchange +) three operator launches.  The step is captured once into a CUDA graph and
+    # replayed (the reference's own -use-graph mode, runtime/hipacc_cu_standalone.hpp:331-356), so the timed region
+    # is not bounded by the Python host; at N > 1 the NCCL send/recv pair of the halo exchange is part of the graph.
+    use_graph = not args.no_graph and not (world > 1 and halo is None)   # NCCL send/recv stays outside graphs
+    launches_per_step = len(OPS) + (1 if halo is not None else 0)
+    step, graph_note = step_direct, "direct launches through hb_local_op"
     if use_graph:
-        step_direct()
+        step_direct()            # also creates the NCCL P2P communicators before capture
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            step_direct()
-
-        def step():
-            graph.replay()
-    else:
-        step = step_direct
+        ok = 1
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+                step_direct()
+        except Exception as e:   # noqa: BLE001 -- fall back to direct launches, on every rank
+            ok = 0
+            sys.stderr.write(f"[rank {rank}] CUDA graph capture failed ({type(e).__name__}: {e}); using direct launches\n")
+        if world > 1:
+            t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            ok = int(t_ok.item())
+        use_graph = bool(ok)
+        if use_graph:
+            step = graph.replay
+            graph_note = "CUDA graph replay of the step (3 operator kernels" + (" + 1 peer-to-peer halo kernel)" if world > 1 else ")")
 
     def sync_all():
         torch.cuda.synchronize()
@@ -228,10 +249,10 @@ def main():
 
     for _ in range(warm):
         step()
-    sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.start()   # before the barrier: its start-up cost must not skew rank 0 against the ranks that wait for its halo rows
+    sync_all()
     n0 = hb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -240,6 +261,8 @@ def main():
     e1.record(stream)
     sync_all()
     ms = e0.elapsed_time(e1)
+    if os.environ.get("HB_BENCH_VERBOSE"):
+        sys.stderr.write(f"[rank {rank}] {ms / steps:.4f} ms per step on this rank\n")
     launches = launches_per_step * steps if use_graph else hb.launch_count() - n0
     clocks = sampler.stop() if sampler else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -297,7 +320,7 @@ def main():
            "api": "hb_image_write + 3 x hb_local_op + 3 x hb_image_read (pinned host buffers)"}
 
     if args.extra:
-        operators = extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream)
+        operators = extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream, args.halo == "p2p")
     else:
         operators = None
 
@@ -314,15 +337,23 @@ def main():
             "config": {"workload": "C2: Sobel-X + Sobel-Y + Laplace 3x3 local operators, float 8192x8192 per GPU, MIRROR boundary",
                        "pixels_per_step": px_per_step, "operators_per_step": len(OPS), "image": f"{W}x{plan.rows} per rank, {W}x{H * world} global",
                        "l2": "inputs 256 MiB + outputs 768 MiB per step exceed the 126 MB L2; no explicit flush",
-                       "halo_exchange": "none (N=1)" if world == 1 else "1 ghost row per side per step via NCCL send/recv inside the timed region",
-                       "launch": "CUDA graph replay of the step (3 kernel nodes)" if use_graph else "direct launches through hb_local_op"},
+                       "halo_exchange": "none (N=1)" if world == 1 else ("1 ghost row per side per step, pushed peer to peer over NVLink by hb_halo_exchange (CUDA IPC, device-side flags) inside the timed region"
+                                         if halo is not None else "1 ghost row per side per step via NCCL send/recv inside the timed region"),
+                       "launch": graph_note},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if operators:
             line["operators"] = operators
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        if halo is not None and rank == 0:
+            n_ex, timed_out = halo.status()
+            if timed_out:
+                sys.stderr.write("WARNING: a halo exchange timed out waiting for a neighbour\n")
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)   # skip interpreter teardown: CUDA graphs / IPC mappings and the NCCL communicator do not need an orderly exit
 
 
 def extra_operators(hb, dev, peak):
@@ -396,7 +427,7 @@ def extra_operators(hb, dev, peak):
     return res
 
 
-def extra_sharded(hb, dev, world, rank, stream):
+def extra_sharded(hb, dev, world, rank, stream, p2p=True):
     """N > 1: the sharded BASELINE configs (strong scaling: the named global image cut into `world` row strips).
     C4 Harris 32768^2 uchar (halo exchange + fused kernel per step), C5 pyramid 16384^2 float, 8 levels (one halo
     exchange per level transition), C3 fused min/max/sum + one all-reduce per scalar.  Device-timed, max over ranks."""
@@ -404,6 +435,22 @@ def extra_sharded(hb, dev, world, rank, stream):
     import torch.distributed as dist
     from hipacc_b200 import _abi as A, masks as M, strips, synth
     res = {}
+
+    def graphed(fn):
+        """capture fn (kernels + NCCL halo exchanges) into a CUDA graph; every rank falls back together"""
+        fn()
+        torch.cuda.synchronize()
+        ok = 1
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                fn()
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            sys.stderr.write(f"[rank {rank}] graph capture failed: {e}\n")
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        return (g.replay, "CUDA graph replay") if int(t_ok.item()) else (fn, "direct launches")
 
     def timeit(fn, reps=5, warm=2):
         for _ in range(warm):
@@ -424,25 +471,35 @@ def extra_sharded(hb, dev, world, rank, stream):
     # C4: Harris on a 32768 x 32768 uchar image, `world` row strips with 2 ghost rows
     Wc, Hc = 32768, 32768
     plan = strips.StripPlan(Wc, Hc, world, rank, radius=2, boundary=A.CLAMP)
-    buf = torch.empty((plan.buffer_rows, Wc), dtype=torch.uint8, device=dev)
+    buf = hb.alloc_image(A.U8, Wc, plan.buffer_rows, device=dev)
     strips.owned(buf, plan).copy_(synth.image_torch("uint8", Wc, plan.rows, seed=4, y0=plan.y0, device=dev))
     out = torch.empty_like(buf)
+    halo = strips.P2PHalo(hb, buf, plan) if p2p else None
 
     def harris_step():
-        strips.exchange_halos(buf, plan)
+        if halo is not None:
+            halo.exchange(stream)
+        else:
+            strips.exchange_halos(buf, plan)
         hb.harris(buf, dst=out, roi=plan.roi(), ghost=plan.ghost(), stream=stream)
-    ms = timeit(harris_step)
-    res["C4_harris_fused_u8_32768x32768_sharded"] = {"Gpx_s": Wc * Hc / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world,
-                                                      "note": f"strong scaling: {plan.rows} rows per rank + 2 ghost rows exchanged per step (NCCL send/recv)"}
+    fn, how = graphed(harris_step) if p2p else (harris_step, "direct launches")
+    ms = timeit(fn)
+    res["C4_harris_fused_u8_32768x32768_sharded"] = {"Gpx_s": Wc * Hc / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world, "launch": how,
+                                                      "note": f"strong scaling: {plan.rows} rows per rank + 2 ghost rows exchanged per step (" + ("peer-to-peer push kernel" if p2p else "NCCL send/recv") + ")"}
     del buf, out
     # C5: 8-level pyramid of a 16384 x 16384 float image on row strips
     Wp = Hp = 16384
-    pg = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev)
-    pl = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev)
+    pg = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev, hb=hb)
+    pl = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev, hb=hb)
+    if p2p:
+        pg.enable_p2p(hb)
+        pl.enable_p2p(hb)
     pg.owned(0).copy_(synth.image_torch("float32", Wp, pg.plans[0].rows, seed=5, y0=pg.plans[0].y0, device=dev))
-    ms = timeit(lambda: strips.pyramid_traverse_strips(hb, pg, pl, M.GAUSS5, stream=stream), reps=3, warm=1)
-    res["C5_pyramid8_f32_16384_sharded"] = {"Gpx_s": Wp * Hp / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world,
-                                            "note": "strong scaling: 14 halo exchanges (4 rows per neighbour) + 14 fused level kernels per traversal"}
+    traverse = lambda: strips.pyramid_traverse_strips(hb, pg, pl, M.GAUSS5, stream=stream)  # noqa: E731
+    fn, how = graphed(traverse) if p2p else (traverse, "direct launches")
+    ms = timeit(fn, reps=3, warm=1)
+    res["C5_pyramid8_f32_16384_sharded"] = {"Gpx_s": Wp * Hp / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world, "launch": how,
+                                            "note": "strong scaling: 21 halo exchanges (4 rows per neighbour, " + ("peer-to-peer push kernels" if p2p else "NCCL send/recv") + ") + 14 fused level kernels per traversal"}
     del pg, pl
     # C3 reductions: per-rank fused min/max/sum partials + all-reduce (weak: 8192 x 8192 per rank)
     f = hb.empty_image(A.F32, 8192, 8192, device=dev)

@@ -57,6 +57,13 @@ def lib():
         L.hb_image_copy.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_image_copy_region.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_stream_synchronize.argtypes = [C.c_void_p]
+        L.hb_ipc_export.argtypes = [C.c_void_p, C.POINTER(A.hb_ipc_mem)]
+        L.hb_ipc_open.argtypes = [C.POINTER(A.hb_ipc_mem), C.POINTER(C.c_void_p)]
+        L.hb_ipc_close.argtypes = [C.c_void_p]
+        L.hb_halo_ctrl_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.hb_halo_ctrl_destroy.argtypes = [C.c_void_p]
+        L.hb_halo_status.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.hb_halo_exchange.argtypes = [C.POINTER(A.hb_halo_desc), C.c_void_p]
         _lib = L
     return _lib
 
@@ -120,6 +127,29 @@ def empty_image(dtype, width, height, device="cuda", align_bytes=256):
     stride = (width + per - 1) // per * per
     buf = torch.empty((height, stride), dtype=torch_dtype(dtype), device=device)
     return buf[:, :width]
+
+
+class _DevArray:
+    """__cuda_array_interface__ carrier so torch can wrap memory the library allocated"""
+
+    def __init__(self, ptr, shape, strides, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "strides": strides, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def alloc_image(dtype, width, height, device="cuda", align_bytes=256):
+    """An image allocated by the LIBRARY (hb_image_create = one cudaMalloc), wrapped as a torch tensor of shape
+    [height, stride].  Unlike a torch allocation its base pointer is a whole CUDA allocation, which is what CUDA IPC
+    (hb_ipc_export, the peer-to-peer halo exchange) needs.  Returns the full-stride tensor; the memory is released
+    when the returned tensor's `hb_owner` is destroyed explicitly (kept alive for the life of the process otherwise)."""
+    import torch
+    v = A.hb_view()
+    with torch.cuda.device(device):
+        _check(lib().hb_image_create(dtype, width, height, align_bytes, C.byref(v)), "hb_image_create")
+    es = A.DTYPE_SIZE[dtype]
+    typestr = {A.U8: "|u1", A.S8: "|i1", A.S16: "<i2", A.S32: "<i4", A.F32: "<f4"}[dtype]
+    t = torch.as_tensor(_DevArray(v.data, (height, v.stride), (v.stride * es, es), typestr), device=device)
+    t.hb_owner = v
+    return t
 
 
 # ----------------------------------------------------------------------------- operators

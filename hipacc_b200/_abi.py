@@ -101,6 +101,22 @@ class hb_pyr_up_desc(C.Structure):
     _fields_ = [("coarse_gaus", hb_view), ("coarse_lap", hb_view), ("fine_gaus", hb_view), ("fine_lap", hb_view)]
 
 
+class hb_ipc_mem(C.Structure):
+    _fields_ = [("handle", C.c_ubyte * 64)]
+
+
+class hb_halo_desc(C.Structure):
+    _fields_ = [
+        ("buf", C.c_void_p), ("pitch_bytes", C.c_size_t), ("row_bytes", C.c_size_t),
+        ("ghost_top", C.c_int), ("rows", C.c_int), ("radius", C.c_int),
+        ("ctrl", C.c_void_p),
+        ("up_buf", C.c_void_p), ("up_ctrl", C.c_void_p), ("up_pitch_bytes", C.c_size_t),
+        ("up_ghost_top", C.c_int), ("up_rows", C.c_int),
+        ("down_buf", C.c_void_p), ("down_ctrl", C.c_void_p), ("down_pitch_bytes", C.c_size_t),
+        ("down_ghost_top", C.c_int),
+    ]
+
+
 def make_view(ptr, dtype, img_w, img_h, stride=None, roi=None, ghost=(0, 0)):
     """Build an hb_view.  roi = (w, h, ox, oy) or None for the whole image."""
     v = hb_view()
@@ -126,4 +142,5 @@ EXPORTS = [
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",
     "hb_harris", "hb_pyr_down", "hb_pyr_up",
+    "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange",
 ]

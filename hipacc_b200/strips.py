@@ -105,6 +105,75 @@ def exchange_halos(buf, plan, group=None):
         w.wait()
 
 
+class P2PHalo:
+    """Peer-to-peer halo exchange of one strip buffer over NVLink (hb_halo_exchange): the ranks swap CUDA IPC handles
+    of their buffers and control blocks once (host side, through torch.distributed), afterwards every exchange is ONE
+    kernel launch per rank that pushes the edge rows into the neighbours' ghost rows and waits on device-side flags.
+    `buf` must come from hipacc_b200.alloc_image (a whole CUDA allocation) with shape [plan.buffer_rows, stride]."""
+
+    def __init__(self, hb, buf, plan, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.hb, self.buf, self.plan = hb, buf, plan
+        self.L = hb.lib()
+        self.desc = None
+        if plan.world == 1 or plan.radius == 0:
+            return
+        L = self.L
+        mem, cmem = A.hb_ipc_mem(), A.hb_ipc_mem()
+        self.ctrl = C.c_void_p()
+        hb._check(L.hb_halo_ctrl_create(C.byref(self.ctrl)), "hb_halo_ctrl_create")
+        hb._check(L.hb_ipc_export(C.c_void_p(buf.data_ptr()), C.byref(mem)), "hb_ipc_export(buffer)")
+        hb._check(L.hb_ipc_export(self.ctrl, C.byref(cmem)), "hb_ipc_export(control block)")
+        es = buf.element_size()
+        mine = {"mem": bytes(mem.handle), "ctrl": bytes(cmem.handle), "gt": plan.ghost_top, "rows": plan.rows,
+                "pitch": buf.stride(0) * es}
+        everyone = [None] * plan.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self._peers = {}
+
+        def open_peer(r):
+            if r not in self._peers:
+                pm, pc = A.hb_ipc_mem(), A.hb_ipc_mem()
+                C.memmove(pm.handle, everyone[r]["mem"], 64)
+                C.memmove(pc.handle, everyone[r]["ctrl"], 64)
+                pb, pk = C.c_void_p(), C.c_void_p()
+                hb._check(L.hb_ipc_open(C.byref(pm), C.byref(pb)), "hb_ipc_open(buffer)")
+                hb._check(L.hb_ipc_open(C.byref(pc), C.byref(pk)), "hb_ipc_open(control block)")
+                self._peers[r] = (pb, pk)
+            return self._peers[r]
+
+        d = A.hb_halo_desc()
+        d.buf, d.pitch_bytes, d.row_bytes = buf.data_ptr(), buf.stride(0) * es, plan.width * es
+        d.ghost_top, d.rows, d.radius = plan.ghost_top, plan.rows, plan.radius
+        d.ctrl = self.ctrl
+        if plan._has_up():
+            pb, pk = open_peer(plan.up())
+            info = everyone[plan.up()]
+            d.up_buf, d.up_ctrl, d.up_pitch_bytes, d.up_ghost_top, d.up_rows = pb, pk, info["pitch"], info["gt"], info["rows"]
+        if plan._has_down():
+            pb, pk = open_peer(plan.down())
+            info = everyone[plan.down()]
+            d.down_buf, d.down_ctrl, d.down_pitch_bytes, d.down_ghost_top = pb, pk, info["pitch"], info["gt"]
+        self.desc = d
+        dist.barrier(group=group)   # every rank has mapped its neighbours before the first push
+
+    def exchange(self, stream=None):
+        import ctypes as C
+        if self.desc is None:
+            return
+        self.hb._check(self.L.hb_halo_exchange(C.byref(self.desc), self.hb.stream_ptr(stream)), "hb_halo_exchange")
+
+    def status(self):
+        """(exchanges completed, timed_out flag) read back from the control block (synchronising)"""
+        import ctypes as C
+        if self.desc is None:
+            return 0, 0
+        n, t = C.c_int(), C.c_int()
+        self.hb._check(self.L.hb_halo_status(self.ctrl, C.byref(n), C.byref(t)), "hb_halo_status")
+        return n.value, t.value
+
+
 def allreduce_minmaxsum(mn, mx, sm, group=None, device=None):
     """Combine per-rank (min, max, sum) partials: one all-reduce per op over a scalar each
     (MIN / MAX exact, SUM in float64)."""
@@ -129,7 +198,7 @@ class StripPyramid:
     mappings of the level transitions are unchanged.  Each level buffer carries `radius` ghost rows per interior
     side: the fused down kernel needs mask/2 + 2 rows of the finer level, the up kernel one row of the coarser."""
 
-    def __init__(self, width, height, depth, world, rank, radius, device, stride_align=64):
+    def __init__(self, width, height, depth, world, rank, radius, device, stride_align=64, hb=None):
         import torch
         assert height % (world << (depth - 1)) == 0 and width % (1 << (depth - 1)) == 0, \
             "sharded pyramid: level-0 strips must be multiples of 2^(depth-1) rows and the width of 2^(depth-1)"
@@ -137,10 +206,23 @@ class StripPyramid:
         self.plans = [StripPlan(width >> l, height >> l, world, rank, radius, A.CLAMP) for l in range(depth)]
         for p in self.plans:
             p.validate()
-        self.bufs = []
+        self.bufs, self.halos = [], None
         for p in self.plans:
             stride = (p.width + stride_align - 1) // stride_align * stride_align
-            self.bufs.append(torch.zeros((p.buffer_rows, stride), dtype=torch.float32, device=device))
+            if hb is None:
+                self.bufs.append(torch.zeros((p.buffer_rows, stride), dtype=torch.float32, device=device))
+            else:   # library allocations: CUDA IPC (peer-to-peer halo exchange) needs whole allocations
+                self.bufs.append(hb.alloc_image(A.F32, stride, p.buffer_rows, device=device, align_bytes=4 * stride_align).zero_())
+
+    def enable_p2p(self, hb, group=None):
+        """map the neighbours' level buffers (CUDA IPC): exchanges become single kernel launches (P2PHalo)"""
+        self.halos = [P2PHalo(hb, b, p, group) for b, p in zip(self.bufs, self.plans)]
+
+    def exchange(self, l, stream=None, group=None):
+        if self.halos is not None:
+            self.halos[l].exchange(stream)
+        else:
+            exchange_many([(self.bufs[l], self.plans[l])], group)
 
     def owned(self, l):
         return owned(self.bufs[l], self.plans[l])[:, :self.plans[l].width]
@@ -185,13 +267,15 @@ def pyramid_up_step(hb, pg, pl, l, stream=None):
     hb.pyr_up(pg.strip(l + 1), pl.strip(l + 1), pg.region(l), pl.region(l), stream=stream)
 
 
-def pyramid_traverse_strips(hb, pg, pl, mask, stream=None, group=None, exchange=exchange_many):
+def pyramid_traverse_strips(hb, pg, pl, mask, stream=None, group=None):
     """The Gaussian / Laplacian pyramid traversal (Gaussian_Laplacian_Pyramid/src/main.cpp:199-248) on row strips:
     one halo exchange (radius rows to each neighbour) before every level transition, kernels unchanged otherwise;
-    results are bit-identical to the unsharded traversal."""
+    results are bit-identical to the unsharded traversal.  Exchanges go peer to peer (one kernel launch each) when
+    the pyramids were set up with enable_p2p(), through NCCL send/recv otherwise."""
     for l in range(1, pg.depth):
-        exchange([(pg.bufs[l - 1], pg.plans[l - 1])], group)
+        pg.exchange(l - 1, stream, group)
         pyramid_down_step(hb, pg, pl, l, mask, stream)
     for l in range(pg.depth - 2, -1, -1):
-        exchange([(pg.bufs[l + 1], pg.plans[l + 1]), (pl.bufs[l + 1], pl.plans[l + 1])], group)
+        pg.exchange(l + 1, stream, group)
+        pl.exchange(l + 1, stream, group)
         pyramid_up_step(hb, pg, pl, l, stream)

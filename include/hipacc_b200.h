@@ -295,6 +295,42 @@ typedef struct {
 } hb_pyr_up_desc;
 int hb_pyr_up(const hb_pyr_up_desc *desc, void *stream);
 
+/* ------------------------------------------------------------------ peer-to-peer halo exchange */
+/*
+ * Row-strip sharding across the GPUs of one box (BASELINE.json: halo rows exchanged peer to peer over
+ * NVLink).  The reference has no multi-device code; these entry points are the B200-native addition.
+ * One process per GPU.  A rank exports its strip buffer and a control block (hb_halo_ctrl_create)
+ * with hb_ipc_export, sends the 64-byte handles to its neighbours (any host channel), and maps
+ * theirs with hb_ipc_open.  hb_halo_exchange then launches ONE kernel that pushes this rank's
+ * `radius` top / bottom owned rows into the neighbours' ghost rows with peer stores and waits
+ * (device side, system-scope flags in the control blocks) until its own ghost rows have arrived
+ * and the previous ones have been consumed.  No host synchronisation, CUDA-graph replayable.
+ * Buffers must be whole allocations (hb_image_create / cudaMalloc base pointers).
+ */
+#define HB_IPC_HANDLE_BYTES 64
+typedef struct { unsigned char handle[HB_IPC_HANDLE_BYTES]; } hb_ipc_mem;
+int hb_ipc_export(const void *device_ptr, hb_ipc_mem *out);
+int hb_ipc_open(const hb_ipc_mem *in, void **peer_ptr);
+int hb_ipc_close(void *peer_ptr);
+int hb_halo_ctrl_create(void **ctrl);
+int hb_halo_ctrl_destroy(void *ctrl);
+/* exchanges completed so far and whether a wait ever timed out (~2 s; a neighbour never arrived) */
+int hb_halo_status(const void *ctrl, int *exchanges, int *timed_out);
+
+typedef struct {
+  void *buf;                 /* this rank's strip buffer, row 0 = first ghost row */
+  size_t pitch_bytes, row_bytes;
+  int ghost_top, rows, radius;
+  void *ctrl;                /* this rank's control block */
+  void *up_buf, *up_ctrl;    /* upper neighbour's buffer / control block (peer pointers) or NULL */
+  size_t up_pitch_bytes;
+  int up_ghost_top, up_rows; /* its layout: my rows land at row up_ghost_top + up_rows */
+  void *down_buf, *down_ctrl;
+  size_t down_pitch_bytes;
+  int down_ghost_top;        /* my rows land at row down_ghost_top - radius */
+} hb_halo_desc;
+int hb_halo_exchange(const hb_halo_desc *desc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
