@@ -201,7 +201,12 @@ def main():
     stream = torch.cuda.Stream(device=dev)       # the stream every kernel of the timed region runs on
     torch.cuda.set_stream(stream)
 
-    halo = strips.P2PHalo(hb, buf, plan) if (world > 1 and args.halo == "p2p") else None
+    halo = None
+    if world > 1 and args.halo == "p2p":
+        try:
+            halo = strips.P2PHalo(hb, buf, plan)   # raises on every rank together if CUDA IPC / peer access is unavailable
+        except RuntimeError as e:
+            sys.stderr.write(f"[rank {rank}] peer-to-peer halo exchange unavailable ({e}); using NCCL send/recv\n")
 
     skip_exchange = bool(int(os.environ.get("HB_BENCH_NO_EXCHANGE", "0")))   # diagnosis only: kernels without the halo exchange
 
@@ -320,7 +325,7 @@ def main():
            "api": "hb_image_write + 3 x hb_local_op + 3 x hb_image_read (pinned host buffers)"}
 
     if args.extra:
-        operators = extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream, args.halo == "p2p")
+        operators = extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream, halo is not None)
     else:
         operators = None
 

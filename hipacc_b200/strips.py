@@ -122,14 +122,23 @@ class P2PHalo:
         L = self.L
         mem, cmem = A.hb_ipc_mem(), A.hb_ipc_mem()
         self.ctrl = C.c_void_p()
-        hb._check(L.hb_halo_ctrl_create(C.byref(self.ctrl)), "hb_halo_ctrl_create")
-        hb._check(L.hb_ipc_export(C.c_void_p(buf.data_ptr()), C.byref(mem)), "hb_ipc_export(buffer)")
-        hb._check(L.hb_ipc_export(self.ctrl, C.byref(cmem)), "hb_ipc_export(control block)")
         es = buf.element_size()
+        # every rank reaches every collective below even if a local CUDA call fails: errors travel with the
+        # gathered objects and all ranks raise together (no rank is left waiting in a collective)
+        err = None
+        try:
+            hb._check(L.hb_halo_ctrl_create(C.byref(self.ctrl)), "hb_halo_ctrl_create")
+            hb._check(L.hb_ipc_export(C.c_void_p(buf.data_ptr()), C.byref(mem)), "hb_ipc_export(buffer)")
+            hb._check(L.hb_ipc_export(self.ctrl, C.byref(cmem)), "hb_ipc_export(control block)")
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {plan.rank}: {e}"
         mine = {"mem": bytes(mem.handle), "ctrl": bytes(cmem.handle), "gt": plan.ghost_top, "rows": plan.rows,
-                "pitch": buf.stride(0) * es}
+                "pitch": buf.stride(0) * es, "err": err}
         everyone = [None] * plan.world
         dist.all_gather_object(everyone, mine, group=group)
+        errs = [o["err"] for o in everyone if o["err"]]
+        if errs:
+            raise RuntimeError("P2PHalo: CUDA IPC export failed: " + "; ".join(errs))
         self._peers = {}
 
         def open_peer(r):
@@ -147,16 +156,23 @@ class P2PHalo:
         d.buf, d.pitch_bytes, d.row_bytes = buf.data_ptr(), buf.stride(0) * es, plan.width * es
         d.ghost_top, d.rows, d.radius = plan.ghost_top, plan.rows, plan.radius
         d.ctrl = self.ctrl
-        if plan._has_up():
-            pb, pk = open_peer(plan.up())
-            info = everyone[plan.up()]
-            d.up_buf, d.up_ctrl, d.up_pitch_bytes, d.up_ghost_top, d.up_rows = pb, pk, info["pitch"], info["gt"], info["rows"]
-        if plan._has_down():
-            pb, pk = open_peer(plan.down())
-            info = everyone[plan.down()]
-            d.down_buf, d.down_ctrl, d.down_pitch_bytes, d.down_ghost_top = pb, pk, info["pitch"], info["gt"]
+        try:
+            if plan._has_up():
+                pb, pk = open_peer(plan.up())
+                info = everyone[plan.up()]
+                d.up_buf, d.up_ctrl, d.up_pitch_bytes, d.up_ghost_top, d.up_rows = pb, pk, info["pitch"], info["gt"], info["rows"]
+            if plan._has_down():
+                pb, pk = open_peer(plan.down())
+                info = everyone[plan.down()]
+                d.down_buf, d.down_ctrl, d.down_pitch_bytes, d.down_ghost_top = pb, pk, info["pitch"], info["gt"]
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {plan.rank}: {e}"
+        status = [None] * plan.world
+        dist.all_gather_object(status, err, group=group)   # also the barrier: every rank has mapped its neighbours before the first push
+        errs = [e for e in status if e]
+        if errs:
+            raise RuntimeError("P2PHalo: mapping a neighbour's memory failed: " + "; ".join(errs))
         self.desc = d
-        dist.barrier(group=group)   # every rank has mapped its neighbours before the first push
 
     def exchange(self, stream=None):
         import ctypes as C
