@@ -392,6 +392,13 @@ def extra_operators(hb, dev, peak):
     g5 = S.gaussian_blur(M.GAUSS5, A.CLAMP)
     entry("C1_gaussian5x5_u8_4096", 4096 * 4096, 2 * 4096 * 4096, timeit(lambda: hb.local_op(g5, u, dst=uo, stream=stream)),
           "bit-exact float mask: FP32-issue bound, 16 MiB image fits L2")
+    # vector pixels: Gaussian_Blur_RGBA's own size, uchar4 (4 B read + 4 B written per pixel)
+    rgba = torch.empty((3024, 4032, 4), dtype=torch.uint8, device=dev)
+    rgba.view(3024, 4032 * 4).copy_(synth.image_torch("uint8", 4032 * 4, 3024, seed=6, device=dev))
+    rgba_o = torch.empty_like(rgba)
+    entry("gaussian5x5_rgba_u8x4_4032x3024", 4032 * 3024, 8 * 4032 * 3024, timeit(lambda: hb.local_op(g5, rgba, dst=rgba_o, stream=stream)),
+          "uchar4 pixels, float4 accumulate per channel: FP32-issue bound (4 channels x 25 taps per pixel)")
+    del rgba, rgba_o
     # C3 bilateral 13x13 float 8192^2 + fused min/max/sum
     f = hb.empty_image(A.F32, 8192, 8192, device=dev)
     f.copy_(synth.image_torch("float32", 8192, 8192, seed=3, scale=255.0, device=dev))

@@ -112,10 +112,28 @@ __host__ __device__ __forceinline__ constexpr int round_up(int a, int b) { retur
 // aligned) take the branch-free vector path; border tiles fetch every element through the boundary
 // mode, so the compute code that follows never sees a boundary.
 // ------------------------------------------------------------------------------------------------
-template <typename TI, typename TS, int ROWS, int TWS, int NTHREADS>
+// CH > 1: the image holds CH interleaved channels per pixel (uchar4); columns count channel ELEMENTS, the boundary
+// window `w` counts PIXELS, so the remap works on the pixel index and keeps the channel.
+template <typename T, int CH>
+__device__ __forceinline__ T fetch_bh_elem(const ImgRef<T> &im, const Window &w, int ex, int y, T cval) {
+    if (CH == 1) return fetch_bh(im, w, ex, y, cval);
+    int px = ex >= 0 ? ex / CH : -((CH - 1 - ex) / CH);   // floor(ex / CH)
+    const int ch = ex - px * CH;
+    if (w.mode == HB_BOUNDARY_CONSTANT) {
+        if (px < w.lo_x || px >= w.hi_x || y < w.lo_y || y >= w.hi_y) return cval;
+    } else {
+        px = remap_idx(px, w.lo_x, w.hi_x, w.mode);
+        y = remap_idx(y, w.lo_y, w.hi_y, w.mode);
+        px = min(max(px, 0), im.iw / CH - 1);
+        y = min(max(y, 0), im.ih - 1);
+    }
+    return im.p[(size_t)y * im.stride + px * CH + ch];
+}
+
+template <typename TI, typename TS, int ROWS, int TWS, int NTHREADS, int CH = 1>
 __device__ __forceinline__ void stage_tile(TS *tile, const TI *__restrict__ in, int in_stride, int in_iw, int in_ih,
                                            const Window w, TI cval, int x_start, int y_start, int tid) {
-    const bool interior = x_start >= w.lo_x && x_start + TWS <= w.hi_x && y_start >= w.lo_y && y_start + ROWS <= w.hi_y;
+    const bool interior = x_start >= w.lo_x * CH && x_start + TWS <= w.hi_x * CH && y_start >= w.lo_y && y_start + ROWS <= w.hi_y;
     const bool aligned = ((reinterpret_cast<uintptr_t>(in) + (size_t)x_start * sizeof(TI)) % (4 * sizeof(TI)) == 0) && (in_stride % 4 == 0);
     if (interior && aligned) {
         constexpr int VPR = TWS / 4;
@@ -132,7 +150,7 @@ __device__ __forceinline__ void stage_tile(TS *tile, const TI *__restrict__ in, 
         ImgRef<TI> im{in, in_stride, in_iw, in_ih};
         for (int e = tid; e < ROWS * TWS; e += NTHREADS) {
             const int r = e / TWS, c = e - r * TWS;
-            tile[e] = (TS)fetch_bh(im, w, x_start + c, y_start + r, cval);
+            tile[e] = (TS)fetch_bh_elem<TI, CH>(im, w, x_start + c, y_start + r, cval);
         }
     }
 }

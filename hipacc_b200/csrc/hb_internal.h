@@ -37,13 +37,23 @@ inline hb_view norm_view(const hb_view &v) {
     return o;
 }
 inline int dtype_size(int dt) {
-    switch (dt) { case HB_U8: case HB_S8: return 1; case HB_U16: case HB_S16: return 2; default: return 4; }
+    switch (dt) { case HB_U8: case HB_S8: return 1; case HB_U16: case HB_S16: return 2; default: return 4; }  // HB_U8X4: 4 bytes per pixel
 }
 inline bool view_ok(const hb_view &v) {
-    return v.data && v.img_width > 0 && v.img_height > 0 && v.stride >= v.img_width && v.dtype >= HB_U8 && v.dtype <= HB_F32 &&
+    return v.data && v.img_width > 0 && v.img_height > 0 && v.stride >= v.img_width && v.dtype >= HB_U8 && v.dtype <= HB_U8X4 &&
            v.offset_x >= 0 && v.offset_y >= 0 && v.offset_x + v.width <= v.img_width && v.offset_y + v.height <= v.img_height &&
            v.ghost_top >= 0 && v.ghost_bottom >= 0 && v.offset_y - v.ghost_top >= 0 &&
            v.offset_y + v.height + v.ghost_bottom <= v.img_height;
+}
+
+// a uchar4 view as the uchar image of its channel elements (4x wider); `unit` = elements per pixel
+inline hb_view as_channels(const hb_view &v) {
+    hb_view o = v;
+    if (v.dtype == HB_U8X4) {
+        o.dtype = HB_U8;
+        o.img_width *= 4; o.stride *= 4; o.width *= 4; o.offset_x *= 4;
+    }
+    return o;
 }
 
 int sm_count();

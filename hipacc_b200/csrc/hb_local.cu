@@ -27,9 +27,11 @@ namespace hb {
 // ------------------------------------------------------------------------------------------------
 constexpr int TW = 128, RPT = 4, BX = 32, BY = 8, TH = BY * RPT;
 
-template <typename TI, typename TS, typename TO, int SX, int SY, int VAR>
+// CH = interleaved channels per pixel (uchar4: 4): columns then count channel elements, horizontal taps are CH
+// elements apart and every thread's 4 adjacent outputs are the 4 channels of one pixel (or 4 pixels for CH = 1).
+template <typename TI, typename TS, typename TO, int SX, int SY, int VAR, int CH = 1>
 __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_constant__ LocalParams p) {
-    constexpr int HX = SX / 2, HY = SY / 2;
+    constexpr int HX = (SX / 2) * CH, HY = SY / 2;
     constexpr int HXP = round_up(HX, 4);
     constexpr int TWS = TW + 2 * HXP;
     constexpr int ROWS = TH + SY - 1;
@@ -40,8 +42,8 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
     const int tid = ty * BX + tx;
     const int gx0 = blockIdx.x * TW, gy0 = blockIdx.y * TH;
 
-    stage_tile<TI, TS, ROWS, TWS, BX * BY>(tile, static_cast<const TI *>(p.in), p.in_stride, p.in_iw, p.in_ih, p.win,
-                                           (TI)cval_of<TS>(p), p.in_ox + gx0 - HXP, p.in_oy + gy0 - HY, tid);
+    stage_tile<TI, TS, ROWS, TWS, BX * BY, CH>(tile, static_cast<const TI *>(p.in), p.in_stride, p.in_iw, p.in_ih, p.win,
+                                               (TI)cval_of<TS>(p), p.in_ox + gx0 - HXP, p.in_oy + gy0 - HY, tid);
     __syncthreads();
 
     const int mode = VAR == 0 ? (int)HB_REDUCE_SUM : p.reduce_mode;
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
                 if (VAR == 1 && !((p.dom[k >> 5] >> (k & 31)) & 1u)) continue;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const TS pix = w[HXP - HX + i + dx];
+                    const TS pix = w[HXP - HX + i + dx * CH];
                     TS v;
                     if (VAR == 0 || p.tap == HB_TAP_MUL) v = mul_rn(coef_of<TS>(p, k), pix);
                     else v = pix;
@@ -142,6 +144,25 @@ __global__ void __launch_bounds__(256) local_generic_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// uchar4 images: the tiled kernel on the 4x wider channel-element image (p.* already in element units, p.win in pixels)
+template <typename TS>
+static int launch_local_x4(const LocalParams &p, bool fast, cudaStream_t s) {
+    dim3 block(BX, BY);
+    dim3 grid((p.is_w + TW - 1) / TW, (p.is_h + TH - 1) / TH);
+#define HB_TILED4(SXV, SYV)                                                                        \
+    if (p.size_x == SXV && p.size_y == SYV) {                                                      \
+        if (fast) local_tiled_kernel<uchar, TS, uchar, SXV, SYV, 0, 4><<<grid, block, 0, s>>>(p);  \
+        else local_tiled_kernel<uchar, TS, uchar, SXV, SYV, 1, 4><<<grid, block, 0, s>>>(p);       \
+        g_launches++;                                                                              \
+        return HB_OK;                                                                              \
+    }
+    HB_TILED4(3, 3)
+    HB_TILED4(5, 5)
+    HB_TILED4(7, 7)
+#undef HB_TILED4
+    return HB_ERR_UNSUPPORTED;
+}
+
 template <typename TI, typename TS, typename TO>
 static int launch_local(const LocalParams &p, bool fast, cudaStream_t s) {
     dim3 block(BX, BY);
@@ -172,6 +193,10 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     HB_REQUIRE(d, HB_ERR_INVALID, "hb_local_op: null descriptor");
     hb_view in = norm_view(d->in), out = norm_view(d->out);
     HB_REQUIRE(view_ok(in) && view_ok(out), HB_ERR_INVALID, "hb_local_op: malformed view");
+    const bool x4 = in.dtype == HB_U8X4;
+    HB_REQUIRE(x4 == (out.dtype == HB_U8X4), HB_ERR_UNSUPPORTED, "hb_local_op: uchar4 input needs uchar4 output (and vice versa)");
+    const int win_lo_x = in.offset_x, win_hi_x = in.offset_x + in.width;   // boundary window in PIXELS
+    if (x4) { in = as_channels(in); out = as_channels(out); }              // everything else in channel elements
     HB_REQUIRE(d->size_x > 0 && d->size_y > 0 && (d->size_x & 1) && (d->size_y & 1) && d->size_x * d->size_y <= kMaxTaps &&
                    d->size_x <= 13 && d->size_y <= 13,
                HB_ERR_UNSUPPORTED, "hb_local_op: mask %dx%d unsupported (odd sizes up to 13x13)", d->size_x, d->size_y);
@@ -183,7 +208,7 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     memset(&p, 0, sizeof(p));
     p.in = in.data; p.out = out.data;
     p.in_stride = in.stride; p.in_iw = in.img_width; p.in_ih = in.img_height;
-    p.win = Window{in.offset_x, in.offset_x + in.width, in.offset_y - in.ghost_top, in.offset_y + in.height + in.ghost_bottom, d->boundary};
+    p.win = Window{win_lo_x, win_hi_x, in.offset_y - in.ghost_top, in.offset_y + in.height + in.ghost_bottom, d->boundary};
     p.in_ox = in.offset_x; p.in_oy = in.offset_y;
     p.out_stride = out.stride; p.out_ox = out.offset_x; p.out_oy = out.offset_y; p.is_w = out.width; p.is_h = out.height;
     p.size_x = d->size_x; p.size_y = d->size_y;
@@ -218,7 +243,10 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     OpScope scope(s, "hb_local_op");
     int rc = HB_ERR_UNSUPPORTED;
     const int it = in.dtype, ot = out.dtype;
-    if (facc) {
+    if (x4) {
+        rc = facc ? launch_local_x4<float>(p, fast, s) : launch_local_x4<int>(p, fast, s);
+        HB_REQUIRE(rc != HB_ERR_UNSUPPORTED, HB_ERR_UNSUPPORTED, "hb_local_op: uchar4 images support 3x3, 5x5 and 7x7 masks; no CPU fallback");
+    } else if (facc) {
         if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, float, uchar>(p, fast, s);
         else if (it == HB_F32 && ot == HB_F32) {
             // hot path: persistent TMA-pipelined kernel (hb_local_tma.cu); anything it does not take runs staged

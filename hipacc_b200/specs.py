@@ -94,11 +94,14 @@ def sobel_u8(mask, boundary=A.CLAMP, out_dtype=A.S32):
                      A.EPI_CAST, (0, 0, 0), out_dtype)
 
 
-def laplace_u8(mask, boundary=A.CLAMP):
-    """uchar -> uchar: sum += 128; min(sum,255); max(sum,0)"""
+def laplace_u8(mask, boundary=A.CLAMP, add=128):
+    """uchar -> uchar: sum += 128; min(sum,255); max(sum,0).
+    uchar4 (Laplace_RGBA): the reference's `int4 += int` takes its left operand BY VALUE (dsl/types.hpp:146-148,
+    runtime/hipacc_types.hpp:173-175), so `sum += 128` has no effect in the DSL, in the sample's own checker and in
+    the emitted CUDA / C++ code alike -- the reference's RGBA result is `add=0`."""
     m = np.asarray(mask, dtype=np.int32)
     return LocalSpec(m.shape[1], m.shape[0], A.REDUCE_DOMAIN, A.SUM, A.TAP_MUL, A.S32, m, None, boundary, 0.0,
-                     A.EPI_ADD_CLAMP_CAST, (128, 0, 255), A.U8)
+                     A.EPI_ADD_CLAMP_CAST, (add, 0, 255), A.U8)
 
 
 def minmax_u8(size_x, size_y, is_max, boundary=A.CLAMP):

@@ -38,7 +38,11 @@ typedef enum {
 } hb_status;
 
 typedef enum {  /* pixel / accumulator types */
-  HB_U8 = 0, HB_S8 = 1, HB_U16 = 2, HB_S16 = 3, HB_S32 = 4, HB_U32 = 5, HB_F32 = 6
+  HB_U8 = 0, HB_S8 = 1, HB_U16 = 2, HB_S16 = 3, HB_S32 = 4, HB_U32 = 5, HB_F32 = 6,
+  /* vector pixel (dsl/types.hpp:56-516): uchar4 = 4 interleaved uchar channels (RGBA); width / stride / offsets count
+   * PIXELS.  Local and point operators treat the channels independently, which is what the DSL's element-wise
+   * float4 / int4 arithmetic and convert_uchar4() do (samples-public/1_Local_Operators/*_RGBA). */
+  HB_U8X4 = 7
 } hb_dtype;
 
 typedef enum {  /* hipacc::Boundary, dsl/image.hpp:46-52 */

@@ -249,6 +249,11 @@ struct Lowering {
 };
 
 namespace detail {
+// boundary constant as the C ABI carries it (a scalar; vector pixels: the x channel, broadcast)
+template <typename T> inline double const_of(const T &v) { return (double)v; }
+#ifndef HIPACC_B200_NO_VECTOR_TYPES
+inline double const_of(const uchar4 &v) { return (double)v.x; }
+#endif
 template <typename T> hb_view in_view(const Accessor<T> &a) { return a.rt().view(); }
 inline int mode_of(Reduce m) { assert(m != Reduce::MEDIAN && "MEDIAN is not implemented"); return (int)m; }
 
@@ -268,7 +273,7 @@ Lowering local(int kind, const Accessor<TI> &in, const MaskBase &shape, const st
     d.in = in_view(in);
     d.kind = kind; d.reduce_mode = mode_of(mode); d.tap = tap; d.acc_dtype = acc_dtype;
     d.size_x = shape.size_x(); d.size_y = shape.size_y();
-    d.boundary = (int)in.bmode; d.boundary_const = (double)in.const_val;
+    d.boundary = (int)in.bmode; d.boundary_const = detail::const_of(in.const_val);
     d.epilogue = epi.kind;
     for (int i = 0; i < 3; ++i) d.epi_p[i] = epi.p[i];
     Lowering L;
@@ -304,7 +309,7 @@ template <typename T> Lowering bilateral(const Accessor<T> &in, const Mask<float
     hb_bilateral_desc d;
     std::memset(&d, 0, sizeof(d));
     d.in = detail::in_view(in);
-    d.size = mask.size_x(); d.sigma_r = sigma_r; d.boundary = (int)in.bmode; d.boundary_const = (double)in.const_val;
+    d.size = mask.size_x(); d.sigma_r = sigma_r; d.boundary = (int)in.bmode; d.boundary_const = detail::const_of(in.const_val);
     Lowering L;
     L.kind = Lowering::BILATERAL;
     L.launch = [d, cf](const hb_view &out, void *stream) mutable {

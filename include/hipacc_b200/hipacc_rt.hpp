@@ -34,6 +34,14 @@ typedef unsigned short ushort;
 typedef unsigned int uint;
 #endif
 
+// vector pixel types of the DSL (dsl/types.hpp:56-100): 4 interleaved channels
+#ifndef HIPACC_B200_NO_VECTOR_TYPES
+struct uchar4 { unsigned char x, y, z, w; };
+struct int4 { int x, y, z, w; };
+struct float4 { float x, y, z, w; };
+inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return uchar4{x, y, z, w}; }
+#endif
+
 namespace hipacc_b200 {
 
 template <typename T> struct dtype_of;
@@ -45,6 +53,9 @@ template <> struct dtype_of<short> { static constexpr int value = HB_S16; };
 template <> struct dtype_of<int> { static constexpr int value = HB_S32; };
 template <> struct dtype_of<unsigned int> { static constexpr int value = HB_U32; };
 template <> struct dtype_of<float> { static constexpr int value = HB_F32; };
+#ifndef HIPACC_B200_NO_VECTOR_TYPES
+template <> struct dtype_of<uchar4> { static constexpr int value = HB_U8X4; };
+#endif
 
 // checkErr (runtime/hipacc_cu.hpp:69-75): the library has already logged the error; execution continues
 inline void check(int rc, const char *what) {

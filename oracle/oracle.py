@@ -152,6 +152,15 @@ def reduce_minmaxsum(img, roi=None):
     return np.float32(o[0]), np.float32(o[1]), np.float32(o[2]), s.value
 
 
+def local_op_x4(spec, img, **kw):
+    """uchar4 image [H, W, 4]: the DSL's float4 / int4 arithmetic and convert_uchar4() are element-wise
+    (dsl/types.hpp:56-516), so a local operator on uchar4 pixels is the scalar operator on each channel plane."""
+    out = np.empty_like(img)
+    for c in range(4):
+        out[..., c] = local_op(spec, np.ascontiguousarray(img[..., c]), **kw)
+    return out
+
+
 def binning(img, num_bins, index_kind=A.BIN_INDEX_SCALE, value_kind=A.BIN_VALUE_ONE, p0=255.0, roi=None):
     """-emit-cpu binning (BINNING_CPU_2D, runtime/hipacc_cpu_red.hpp:70-128) -> uint32[num_bins]"""
     d = A.hb_binning_desc()
@@ -334,6 +343,24 @@ def ref_global_reduce_f32(img, op, roi=None):
     _check(ref_lib().ref_global_reduce_f32(_p(img, C.c_float), img.shape[1], img.shape[0], op,
                                            _roi8(roi, None), C.byref(r)), "ref_global_reduce_f32")
     return np.float32(r.value)
+
+
+def ref_gaussian_rgba(img, mask, boundary):
+    """sample GaussianBlur of Gaussian_Blur_RGBA (Kernel<uchar4>, float4 accumulate) executed by the reference DSL"""
+    out = np.zeros_like(img)
+    m = np.ascontiguousarray(mask, np.float32)
+    _check(ref_lib().ref_gaussian_rgba(_p(img, C.c_ubyte), _p(out, C.c_ubyte), img.shape[1], img.shape[0], _p(m, C.c_float),
+                                       m.shape[1], m.shape[0], boundary), "ref_gaussian_rgba")
+    return out
+
+
+def ref_laplace_rgba(img, mask, boundary):
+    """sample LaplaceFilter of Laplace_RGBA (Kernel<uchar4>, int4 accumulate, +128 clamp) executed by the reference DSL"""
+    out = np.zeros_like(img)
+    m = np.ascontiguousarray(mask, np.int32)
+    _check(ref_lib().ref_laplace_rgba(_p(img, C.c_ubyte), _p(out, C.c_ubyte), img.shape[1], img.shape[0], _p(m, C.c_int),
+                                      m.shape[0], boundary), "ref_laplace_rgba")
+    return out
 
 
 def ref_sample_histogram_f32(img, num_bins):

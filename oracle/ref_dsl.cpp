@@ -100,6 +100,23 @@ namespace smp_box {
 #undef WIDTH
 #undef HEIGHT
 #undef IMAGE
+namespace smp_gauss_rgba {
+#include "1_Local_Operators/Gaussian_Blur_RGBA/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_laplace_rgba {
+#include "1_Local_Operators/Laplace_RGBA/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef SIZE
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
 namespace smp_hist {
 #include "2_Global_Operators/Histogram/src/main.cpp"
 }
@@ -663,6 +680,45 @@ int ref_sample_reduce_sum_f32(const float *in, int w, int h, float *result) {
     smp_redsum::Reduction k(is, acc);
     k.execute();
     *result = k.reduced_data();
+    return 0;
+}
+
+// -------------------------------------------------------------------- vector pixel types (uchar4)
+// sample GaussianBlur of Gaussian_Blur_RGBA (src/main.cpp:49-67): Kernel<uchar4>, float4 accumulate, convert_uchar4(sum + 0.5f)
+int ref_gaussian_rgba(const uchar *in, uchar *out, int w, int h, const float *coef, int sx, int sy, int bmode) {
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<float, SY_, SX_> mh(coef);                                     \
+        Image<uchar4> I(w, h, reinterpret_cast<uchar4 *>(const_cast<uchar *>(in))); \
+        Image<uchar4> O(w, h, reinterpret_cast<uchar4 *>(out));                   \
+        Mask<float> mask(mh.arr);                                                 \
+        BoundaryCondition<uchar4> bc = make_bc(I, mask, bmode);                   \
+        Accessor<uchar4> acc(bc);                                                 \
+        IterationSpace<uchar4> is(O);                                             \
+        smp_gauss_rgba::GaussianBlur k(is, acc, mask);                            \
+        k.execute();                                                              \
+        std::memcpy(out, O.data(), (size_t)4 * w * h);                            \
+    }
+    DISPATCH_SIZE(sx, sy, CALL);
+#undef CALL
+    return 0;
+}
+// sample LaplaceFilter of Laplace_RGBA (src/main.cpp:49-72): Kernel<uchar4>, int4 accumulate over the Domain, +128, clamp
+int ref_laplace_rgba(const uchar *in, uchar *out, int w, int h, const int *coef, int size, int bmode) {
+#define CALL(SX_, SY_) {                                                          \
+        MaskHolder<int, SY_, SX_> mh(coef);                                       \
+        Image<uchar4> I(w, h, reinterpret_cast<uchar4 *>(const_cast<uchar *>(in))); \
+        Image<uchar4> O(w, h, reinterpret_cast<uchar4 *>(out));                   \
+        Mask<int> mask(mh.arr);                                                   \
+        Domain dom(mask);                                                         \
+        BoundaryCondition<uchar4> bc = make_bc(I, mask, bmode);                   \
+        Accessor<uchar4> acc(bc);                                                 \
+        IterationSpace<uchar4> is(O);                                             \
+        smp_laplace_rgba::LaplaceFilter k(is, acc, dom, mask);                    \
+        k.execute();                                                              \
+        std::memcpy(out, O.data(), (size_t)4 * w * h);                            \
+    }
+    DISPATCH_SIZE(size, size, CALL);
+#undef CALL
     return 0;
 }
 

@@ -20,6 +20,14 @@ U8_SHAPE = (45, 70)
 F32_SHAPE = (39, 66)
 HARRIS_SHAPE = (96, 128)
 PYR_CASES = [(64, 96, 4, 5), (50, 77, 3, 3)]
+RGBA_SHAPE = (37, 53)
+
+
+def rgba_image(h, w, seed=11):
+    """uchar4 image as uint8 [h, w, 4] (channels interleaved)"""
+    return np.ascontiguousarray(synth.image_np("uint8", w * 4, h, seed=seed).reshape(h, w, 4))
+
+
 HIST_SHAPE = (61, 83)
 HIST_BINS = (256, 64, 1000)
 

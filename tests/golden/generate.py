@@ -83,7 +83,28 @@ def hist():
     print("wrote", len(out), "arrays to reference_hist.npz")
 
 
+RGBA_SHAPE = (37, 53)
+
+
+def rgba():
+    """reference_rgba.npz: the RGBA samples' kernels (Kernel<uchar4>) executed by the reference DSL."""
+    out = {}
+    img = np.ascontiguousarray(synth.image_np("uint8", RGBA_SHAPE[1] * 4, RGBA_SHAPE[0], seed=11).reshape(RGBA_SHAPE[0], RGBA_SHAPE[1], 4))
+    for b in (A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT):
+        for sz in (3, 5):
+            out[f"gauss_rgba_{sz}_{b}"] = O.ref_gaussian_rgba(img, M.GAUSS[sz], b)
+        out[f"laplace_rgba_3_{b}"] = O.ref_laplace_rgba(img, M.LAPLACE3, b)
+        out[f"laplace_rgba_5_{b}"] = O.ref_laplace_rgba(img, M.LAPLACE5, b)
+    np.savez_compressed(os.path.join(HERE, "reference_rgba.npz"), **out)
+    print("wrote", len(out), "arrays to reference_rgba.npz")
+
+
 if __name__ == "__main__":
-    if "--only-hist" not in sys.argv:
+    if "--only-hist" in sys.argv:
+        hist()
+    elif "--only-rgba" in sys.argv:
+        rgba()
+    else:
         main()
-    hist()
+        hist()
+        rgba()

@@ -26,7 +26,7 @@ def dev(hb):
 def to_dev(hb, a, dev, padded=True):
     import torch
     t = torch.from_numpy(np.ascontiguousarray(a))
-    if not padded:
+    if not padded or a.ndim == 3:   # uchar4 images [H, W, 4]: dense
         return t.to(dev)
     img = hb.empty_image(A.NUMPY_DTYPE[a.dtype.name], a.shape[1], a.shape[0], device=dev)
     img.copy_(t)
@@ -318,6 +318,69 @@ def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
             roi = (W, y1 - y0, 0, g0)
             out = hb.harris(to_dev(hb, strip, dev), roi=roi, ghost=(g0, g1))
             np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
+
+
+# ------------------------------------------------------------------ vector pixel types (uchar4)
+@pytest.mark.parametrize("b", [A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT])
+def test_rgba_local_ops_vs_golden(hb, dev, b):
+    import os
+    g = np.load(os.path.join(os.path.dirname(cases.GOLDEN_PATH), "reference_rgba.npz"))
+    img = to_dev(hb, cases.rgba_image(*cases.RGBA_SHAPE), dev)
+    for sz in (3, 5):
+        np.testing.assert_array_equal(to_np(hb.local_op(S.gaussian_blur(M.GAUSS[sz], b), img)), g[f"gauss_rgba_{sz}_{b}"])
+    np.testing.assert_array_equal(to_np(hb.local_op(S.laplace_u8(M.LAPLACE3, b, add=0), img)), g[f"laplace_rgba_3_{b}"])
+    np.testing.assert_array_equal(to_np(hb.local_op(S.laplace_u8(M.LAPLACE5, b, add=0), img)), g[f"laplace_rgba_5_{b}"])
+
+
+@pytest.mark.parametrize("shape", [(300, 517), (33, 40), (2, 3), (1, 1), (131, 1024)])
+@pytest.mark.parametrize("b", [A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT, A.UNDEFINED])
+def test_rgba_local_ops_vs_oracle(hb, oracle, dev, shape, b):
+    """several 128-element (32-pixel) tiles, partial tiles, images smaller than the halo; Gaussian 7x7 (float4
+    accumulate), Laplace 5x5 (int4 accumulate over the Domain), dilate 3x3 (max over the Domain)"""
+    if b == A.UNDEFINED and min(shape) < 8:
+        pytest.skip("UNDEFINED reads outside tiny images are unspecified")
+    h, w = shape
+    img = cases.rgba_image(h, w, seed=17)
+    d = to_dev(hb, img, dev)
+    for spec in (S.gaussian_blur(M.GAUSS[7], b), S.laplace_u8(M.LAPLACE5, b), S.minmax_u8(3, 3, True, b)):
+        got, want = to_np(hb.local_op(spec, d)), oracle.local_op_x4(spec, img)
+        if b == A.UNDEFINED:   # only interior pixels are defined
+            r = spec.size_y // 2
+            got, want = got[r:h - r, r:w - r], want[r:h - r, r:w - r]
+        np.testing.assert_array_equal(got, want)
+
+
+def test_rgba_point_ops_and_padded_rows(hb, oracle, dev):
+    import torch
+    img = cases.rgba_image(77, 130, seed=19)
+    a = to_dev(hb, img, dev)
+    np.testing.assert_array_equal(to_np(hb.point_op(A.POINT_COPY, [a])), img)
+    b2 = to_dev(hb, cases.rgba_image(77, 130, seed=20), dev)
+    want = (img.astype(np.int32) + to_np(b2).astype(np.int32)).astype(np.uint8)    # uchar4 + uchar4 wraps per channel
+    np.testing.assert_array_equal(to_np(hb.point_op(A.POINT_ADD, [a, b2])), want)
+    # rows padded to 256 bytes (stride 192 px for 130): the view's stride counts pixels
+    buf = torch.zeros((77, 192, 4), dtype=torch.uint8, device=dev)
+    buf[:, :130] = a
+    spec = S.gaussian_blur(M.GAUSS[5], A.MIRROR)
+    np.testing.assert_array_equal(to_np(hb.local_op(spec, buf[:, :130])), oracle.local_op_x4(spec, img))
+
+
+def test_rgba_full_size_sample_shape(hb, oracle, dev):
+    """Gaussian_Blur_RGBA's own size (4032 x 3024 uchar4): windows against the per-channel oracle"""
+    import torch
+    h, w = 3024, 4032
+    img = torch.from_numpy(cases.rgba_image(h, w, seed=23)).to(dev)
+    spec = S.gaussian_blur(M.GAUSS[5], A.CLAMP)
+    out = hb.local_op(spec, img)
+    for (y0, x0) in ((0, 0), (h - 64, w - 96), (1500, 2000), (0, w - 96), (h - 64, 0)):
+        win = np.ascontiguousarray(to_np(img[max(y0 - 2, 0):y0 + 66, max(x0 - 2, 0):x0 + 98]))
+        ref = oracle.local_op_x4(spec, win)
+        oy, ox = y0 - max(y0 - 2, 0), x0 - max(x0 - 2, 0)
+        # compare the part of the window whose 5x5 neighbourhood lies inside the window or at a true image border
+        ys = slice(oy if y0 > 0 else 0, oy + 62 if y0 + 66 < h else None)
+        xs = slice(ox if x0 > 0 else 0, ox + 94 if x0 + 98 < w else None)
+        got = to_np(out[max(y0 - 2, 0):y0 + 66, max(x0 - 2, 0):x0 + 98])
+        np.testing.assert_array_equal(got[ys, xs], ref[ys, xs])
 
 
 # ------------------------------------------------------------------ binning / histogram

@@ -84,6 +84,19 @@ def test_global_reduce_vs_golden(oracle):
     assert abs(s64 - f32.astype(np.float64).sum()) <= 1e-9 * abs(s64)
 
 
+@pytest.mark.parametrize("b", [A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT])
+def test_rgba_vs_golden(oracle, b):
+    """uchar4 local operators (Gaussian_Blur_RGBA, Laplace_RGBA executed by the reference DSL) == the scalar operator
+    on each channel plane: the per-channel claim the CUDA uchar4 path rests on."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(cases.GOLDEN_PATH), "reference_rgba.npz"))
+    img = cases.rgba_image(*cases.RGBA_SHAPE)
+    for sz in (3, 5):
+        np.testing.assert_array_equal(oracle.local_op_x4(S.gaussian_blur(M.GAUSS[sz], b), img), g[f"gauss_rgba_{sz}_{b}"])
+    np.testing.assert_array_equal(oracle.local_op_x4(S.laplace_u8(M.LAPLACE3, b, add=0), img), g[f"laplace_rgba_3_{b}"])
+    np.testing.assert_array_equal(oracle.local_op_x4(S.laplace_u8(M.LAPLACE5, b, add=0), img), g[f"laplace_rgba_5_{b}"])
+
+
 def test_histogram_vs_golden(oracle):
     """Histogram sample (binning() + binned_data()) executed by the reference DSL -> tests/golden/reference_hist.npz"""
     import os
