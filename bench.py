@@ -191,11 +191,12 @@ def main():
     # ---- data: this rank's strip of the global 8192 x (8192*world) image, resident in HBM
     plan = strips.StripPlan(W, H * world, world, rank, radius=1, boundary=A.MIRROR)
     plan.validate()
-    stride = (W + 63) // 64 * 64
+    pad = int(os.environ.get("HB_BENCH_ROW_PAD", "0"))   # experiment: extra floats per row (row pitch not a power of two)
+    stride = (W + 63) // 64 * 64 + pad
     buf = hb.alloc_image(A.F32, stride, plan.buffer_rows, device=dev)   # a whole CUDA allocation: exportable through CUDA IPC
     strips.owned(buf, plan)[:, :W] = synth.image_torch("float32", W, plan.rows, seed=2, y0=plan.y0, device=dev)
     src = buf[:, :W]
-    outs = [hb.empty_image(A.F32, W, plan.buffer_rows, device=dev) for _ in OPS]
+    outs = [hb.empty_image(A.F32, W + pad, plan.buffer_rows, device=dev)[:, :W] for _ in OPS]
     specs = specs_for_workload()
     roi, ghost = plan.roi(), plan.ghost()
     stream = torch.cuda.Stream(device=dev)       # the stream every kernel of the timed region runs on

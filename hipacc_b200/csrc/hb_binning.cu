@@ -183,8 +183,7 @@ static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStre
     const int npv = v.dtype == HB_F32 ? 4 : 16;
     const long long cpr = (v.width / npv + HT * HU - 1) / (HT * HU);
     const long long chunks = (cpr < 1 ? 1 : cpr) * v.height;
-    const long long cap = (long long)sm_count() * (smem > 16 * 1024 ? 4 : 8);
-    const int blocks = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+    const int blocks = (int)stream_grid(chunks, smem > 16 * 1024 ? 4 : 16);
     int rc = check_cuda(cudaMemsetAsync(bins_dev, 0, sizeof(unsigned) * d->num_bins, s), "cudaMemsetAsync(bins)");
     if (rc) return rc;
     if (v.dtype == HB_F32) dispatch_binning<float>(p, fastdiv, blocks, smem, s);

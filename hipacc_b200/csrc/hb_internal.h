@@ -57,6 +57,10 @@ inline hb_view as_channels(const hb_view &v) {
 }
 
 int sm_count();
+// grid of a streaming kernel that walks `chunks` work units: `per_sm` CTAs per SM (tuning override: HB_STREAM_CTAS_PER_SM,
+// 0 = one CTA per chunk).  Measured on B200 (tools/probe/copy_probe.cu): a one-shot grid streams ~9 % faster than a
+// persistent grid whose CTAs march over memory in lockstep.
+long long stream_grid(long long chunks, int per_sm);
 
 }  // namespace hb
 

@@ -4,12 +4,13 @@
 // Gaussians of the pyramid (C5).  It replaces the generated Hipacc CUDA kernel for such operators
 // (lib/Rewrite/Rewrite.cpp:2726-2883, lib/AST/ASTTranslate.cpp:510-1197).
 //
-//   * persistent grid: (SM count x resident CTAs) CTAs walk the 128 x TH output tiles in row-major order;
+//   * one CTA per 128 x TH output tile, handed out by the hardware block scheduler (a persistent grid with a multi-
+//     stage ring was measured 22 % slower: its CTAs march over memory in lockstep, see launch_variant);
 //   * the input box (tile + halo) of an INTERIOR tile is fetched by one thread with a single
-//     cp.async.bulk.tensor.2d (TMA) into one of two shared-memory stages and completes on an mbarrier, so
-//     the copy of tile i+1 overlaps the arithmetic of tile i and no thread spends instructions on staging;
-//     BORDER tiles (box crosses the accessor's boundary window) are staged by all threads through the
-//     boundary-mode index remap (lib/AST/BorderHandling.cpp:41-120) -- same compute code afterwards;
+//     cp.async.bulk.tensor.2d (TMA) into shared memory and completes on an mbarrier, so no thread spends
+//     instructions on staging; the copy overlaps the arithmetic of the co-resident CTAs;
+//     BORDER tiles (box crosses the accessor's boundary window) get their out-of-window cells patched by all threads
+//     through the boundary-mode index remap (lib/AST/BorderHandling.cpp:41-120) -- same compute code afterwards;
 //   * each thread owns 4 adjacent pixels x RPT rows and walks the staged rows once (row-stationary), taps
 //     are folded per pixel in row-major order with separately rounded multiply and add, first visited tap
 //     initialises (dsl/kernel.hpp:241-296): results are bit-identical to the DSL's sequential fold;
@@ -47,6 +48,7 @@ HB_CONST_MASK(MaskSobel3X, 9, -1, 0, 1, -2, 0, 2, -1, 0, 1)
 HB_CONST_MASK(MaskSobel3Y, 9, -1, -2, -1, 0, 0, 0, 1, 2, 1)
 HB_CONST_MASK(MaskLaplace3D, 9, 2, 0, 2, 0, -8, 0, 2, 0, 2)
 HB_CONST_MASK(MaskLaplace3N, 9, 0, 1, 0, 1, -4, 1, 0, 1, 0)
+HB_CONST_MASK(MaskIdentity3, 9, 0, 0, 0, 0, 1, 0, 0, 0, 0)   // data-movement ceiling of the pipeline (tools/repro_local.py)
 HB_CONST_MASK(MaskSobel5X, 25, -1, -2, 0, 2, 1, -4, -8, 0, 8, 4, -6, -12, 0, 12, 6, -4, -8, 0, 8, 4, -1, -2, 0, 2, 1)
 HB_CONST_MASK(MaskSobel5Y, 25, -1, -4, -6, -4, -1, -2, -8, -12, -8, -2, 0, 0, 0, 0, 0, 2, 8, 12, 8, 2, 1, 4, 6, 4, 1)
 HB_CONST_MASK(MaskLaplace5, 25, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, -24, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1)
@@ -242,11 +244,22 @@ int launch_variant(const LocalParams &p, cudaStream_t s) {
     const int ntx = (p.is_w + TW - 1) / TW, nty = (p.is_h + G::TH - 1) / G::TH;
     const long long ntiles = (long long)ntx * nty;
     if (ntiles > 0x7fffffffLL) return HB_ERR_UNSUPPORTED;
-    long long grid = (long long)sm_count() * ctas_per_sm;
+    // One tile per CTA by default: measured on B200 (profiles/r1p_tma_grid_sweep.txt), a grid of ntiles CTAs that the
+    // block scheduler hands out as CTAs retire streams at the HBM copy peak (809 Gpx/s), while a persistent grid of
+    // resident CTAs marching over the tiles in lockstep reaches 636 Gpx/s with the same kernel -- reads and writes of
+    // all SMs fall into phase.  HB_TMA_GRID_MULT = m > 0 restores a capped grid of m x (resident CTAs) for comparison;
+    // the kernel's tile loop and mbarrier ring handle either.
+    static int grid_mult = -1;
+    if (grid_mult < 0) {
+        const char *e = getenv("HB_TMA_GRID_MULT");
+        grid_mult = e ? atoi(e) : 0;
+        if (grid_mult < 0) grid_mult = 0;
+    }
+    long long grid = grid_mult ? (long long)sm_count() * ctas_per_sm * grid_mult : ntiles;
     if (grid > ntiles) grid = ntiles;
     static int stream_stores = -1;
     if (stream_stores < 0) {
-        const char *e = getenv("HB_TMA_STCS");
+        const char *e = getenv("HB_TMA_STCS");   // tuning knob: st.cs for the output (no measurable effect)
         stream_stores = e ? atoi(e) : 0;
     }
     kern<<<(unsigned)grid, dim3(32, BY), G::SMEM_BYTES, s>>>(p, tmap, ntx, (int)ntiles, stream_stores);
@@ -280,7 +293,9 @@ int launch_shape(const LocalParams &p, cudaStream_t s) {
     case 3: return launch_variant<SX, SY, MASK, 4, 8, 6>(p, s);
     case 4: return launch_variant<SX, SY, MASK, 8, 4, 4>(p, s);
 #endif
-    default: return launch_variant<SX, SY, MASK, 4, 8, 4>(p, s);
+    case 6: return launch_variant<SX, SY, MASK, 4, 8, 2>(p, s);
+    case 7: return launch_variant<SX, SY, MASK, 4, 8, 4>(p, s);   // the 4-stage ring of the persistent design
+    default: return launch_variant<SX, SY, MASK, 4, 8, 1>(p, s);  // one stage: with one tile per CTA the overlap comes from the co-resident CTAs
     }
 }
 
@@ -300,6 +315,7 @@ int launch_local_tma_f32(const LocalParams &p, bool all_taps_visited, cudaStream
         if (mask_equals<MaskSobel3Y>(p)) return launch_shape<3, 3, MaskSobel3Y>(p, s);
         if (mask_equals<MaskLaplace3D>(p)) return launch_shape<3, 3, MaskLaplace3D>(p, s);
         if (mask_equals<MaskLaplace3N>(p)) return launch_shape<3, 3, MaskLaplace3N>(p, s);
+        if (mask_equals<MaskIdentity3>(p)) return launch_shape<3, 3, MaskIdentity3>(p, s);
         if (all_taps_visited) return launch_shape<3, 3, MaskRuntime>(p, s);
     } else if (p.size_x == 5) {
         if (mask_equals<MaskSobel5X>(p)) return launch_shape<5, 5, MaskSobel5X>(p, s);

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) point_kernel(const __grid_constant__ Poin
 // 4-pixel vectors; every thread first issues its PU independent vector loads per input (PU x NIN x 16 bytes
 // in flight for float), then evaluates and stores.  OP and NIN are compile-time so the body is straight-line.
 constexpr int PT = 256, PU = 4;
+constexpr int kStreamCtasPerSm = 0;   // one CTA per chunk (measured: 803 vs 707 Gpx/s for the persistent grid, tools/stream_grid_sweep.sh)
 
 template <typename T> __device__ __forceinline__ void load4_stream(const T *p, T (&v)[4]) {
     typedef typename Vec4<T>::type V;
@@ -175,9 +176,7 @@ template <typename TI, typename TO, int OP, int NIN>
 static void launch_stream(const PointParams &p, cudaStream_t s) {
     const int nvec = p.is_w / 4;
     const int cpr = nvec > 0 ? (nvec + PT * PU - 1) / (PT * PU) : 1;
-    long long blocks = (long long)cpr * p.is_h;
-    const long long cap = (long long)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
-    if (blocks > cap) blocks = cap;
+    const long long blocks = stream_grid((long long)cpr * p.is_h, kStreamCtasPerSm);
     point_stream_kernel<TI, TO, OP, NIN><<<(unsigned)blocks, PT, 0, s>>>(p);
 }
 

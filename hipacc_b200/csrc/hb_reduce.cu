@@ -222,8 +222,7 @@ static int reduce_grid(long long units) {
 static int launch_mms(const hb_view &v, void *result_dev, cudaStream_t s) {
     const long long cpr = (v.width / 4 + CHUNK_V - 1) / CHUNK_V;
     const long long chunks = (cpr < 1 ? 1 : cpr) * v.height;
-    const long long cap = (long long)sm_count() * 8;  // persistent: 8 CTAs of 256 threads per SM
-    const int blocks = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+    const int blocks = (int)stream_grid(chunks, 16);   // measured best of 8 / 16 / 32 / 64 / one-shot (tools/stream_grid_sweep.sh)
     Scratch *sc = nullptr;
     int rc = get_scratch(&sc, blocks);
     if (rc) return rc;

@@ -82,6 +82,19 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+long long stream_grid(long long chunks, int per_sm) {
+    static int override_ = -2;
+    if (override_ == -2) {
+        const char *e = getenv("HB_STREAM_CTAS_PER_SM");
+        override_ = e ? atoi(e) : -1;
+    }
+    if (override_ >= 0) per_sm = override_;
+    if (chunks < 1) chunks = 1;
+    if (per_sm <= 0) return chunks;
+    const long long cap = (long long)sm_count() * per_sm;
+    return chunks < cap ? chunks : cap;
+}
+
 bool tma_addressable(const void *base, int dtype, int stride_px) {
     const size_t es = dtype_size(dtype);
     return (reinterpret_cast<uintptr_t>(base) % 16 == 0) && (((size_t)stride_px * es) % 16 == 0);
