@@ -513,7 +513,7 @@ def extra_sharded(hb, dev, world, rank, stream, p2p=True):
     fn, how = graphed(traverse) if p2p else (traverse, "direct launches")
     ms = timeit(fn, reps=3, warm=1)
     res["C5_pyramid8_f32_16384_sharded"] = {"Gpx_s": Wp * Hp / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world, "launch": how,
-                                            "note": "strong scaling: 21 halo exchanges (4 rows per neighbour, " + ("peer-to-peer push kernels" if p2p else "NCCL send/recv") + ") + 14 fused level kernels per traversal"}
+                                            "note": "strong scaling: 14 halo exchange launches (4 rows per neighbour, " + ("peer-to-peer push kernels" if p2p else "NCCL send/recv") + ") + 14 fused level kernels per traversal"}
     del pg, pl
     # C3 reductions: per-rank fused min/max/sum partials + all-reduce (weak: 8192 x 8192 per rank)
     f = hb.empty_image(A.F32, 8192, 8192, device=dev)
@@ -522,14 +522,10 @@ def extra_sharded(hb, dev, world, rank, stream, p2p=True):
 
     def reduce_step():
         hb.reduce_minmaxsum_async(f, part, stream=stream)
-        mm = part[:2].clone()
-        sm = part[2:4].view(torch.float64).clone()
-        dist.all_reduce(mm[0:1], op=dist.ReduceOp.MIN)
-        dist.all_reduce(mm[1:2], op=dist.ReduceOp.MAX)
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        strips.allgather_minmaxsum(part)        # one 16-byte all-gather + local fold
     ms = timeit(reduce_step)
     res["C3_reduce_minmaxsum_f32_8192_per_rank_allreduce"] = {"Gpx_s": 8192 * 8192 * world / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world,
-                                                              "note": "weak scaling: one pass over HBM per rank + 3 scalar all-reduces (NCCL)"}
+                                                              "note": "weak scaling: one pass over HBM per rank + one 16-byte NCCL all-gather of the {min, max, sum} partials"}
     return res
 
 

@@ -142,5 +142,5 @@ EXPORTS = [
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",
     "hb_harris", "hb_pyr_down", "hb_pyr_up",
-    "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange",
+    "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange", "hb_halo_exchange_batch",
 ]

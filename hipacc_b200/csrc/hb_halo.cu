@@ -64,7 +64,15 @@ __device__ __forceinline__ void push_rows(unsigned char *dst, size_t dpitch, con
     }
 }
 
-__global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_constant__ HaloParams p) {
+constexpr int kMaxHalo = 4;
+struct HaloBatch {
+    HaloParams p[kMaxHalo];
+};
+
+// one CTA per strip buffer of the batch (e.g. the Gaussian and the Laplacian level of a pyramid transition): the
+// exchanges of a batch run concurrently in one launch
+__global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_constant__ HaloBatch batch) {
+    const HaloParams &p = batch.p[blockIdx.x];
     const int e = p.ctrl[0];   // read by every thread before thread 0 advances it (barriers below)
     if (threadIdx.x == 0) {
         // my ghost rows of exchange e-1 are consumed: the neighbours may overwrite them
@@ -137,14 +145,13 @@ extern "C" int hb_halo_status(const void *ctrl, int *exchanges, int *timed_out) 
     return rc;
 }
 
-extern "C" int hb_halo_exchange(const hb_halo_desc *d, void *stream) {
+static int fill_halo_params(const hb_halo_desc *d, HaloParams &p) {
     HB_REQUIRE(d && d->buf && d->ctrl, HB_ERR_INVALID, "hb_halo_exchange: null buffer / control block");
     HB_REQUIRE(d->radius > 0 && d->rows >= d->radius && d->row_bytes > 0 && d->pitch_bytes >= d->row_bytes, HB_ERR_INVALID,
                "hb_halo_exchange: bad geometry (radius %d, rows %d)", d->radius, d->rows);
     HB_REQUIRE((d->up_buf == nullptr) == (d->up_ctrl == nullptr) && (d->down_buf == nullptr) == (d->down_ctrl == nullptr), HB_ERR_INVALID,
                "hb_halo_exchange: a neighbour needs both its buffer and its control block");
     HB_REQUIRE(!d->up_buf || d->ghost_top == d->radius, HB_ERR_INVALID, "hb_halo_exchange: ghost_top must equal the radius when an upper neighbour exists");
-    HaloParams p;
     memset(&p, 0, sizeof(p));
     p.buf = static_cast<unsigned char *>(d->buf); p.pitch = d->pitch_bytes; p.row_bytes = d->row_bytes;
     p.gt = d->ghost_top; p.rows = d->rows; p.R = d->radius;
@@ -158,9 +165,22 @@ extern "C" int hb_halo_exchange(const hb_halo_desc *d, void *stream) {
         p.down_pitch = d->down_pitch_bytes; p.down_ctrl = static_cast<int *>(d->down_ctrl);
     }
     p.ctrl = static_cast<int *>(d->ctrl);
+    return HB_OK;
+}
+
+extern "C" int hb_halo_exchange_batch(const hb_halo_desc *const *descs, int n, void *stream) {
+    HB_REQUIRE(descs && n >= 1 && n <= kMaxHalo, HB_ERR_INVALID, "hb_halo_exchange_batch: 1..%d descriptors", kMaxHalo);
+    HaloBatch b;
+    memset(&b, 0, sizeof(b));
+    for (int i = 0; i < n; ++i) {
+        const int rc = fill_halo_params(descs[i], b.p[i]);
+        if (rc) return rc;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_halo_exchange");
-    halo_exchange_kernel<<<1, 1024, 0, s>>>(p);
+    halo_exchange_kernel<<<n, 1024, 0, s>>>(b);
     g_launches++;
     return scope.finish();
 }
+
+extern "C" int hb_halo_exchange(const hb_halo_desc *d, void *stream) { return hb_halo_exchange_batch(&d, 1, stream); }

@@ -180,6 +180,16 @@ class P2PHalo:
             return
         self.hb._check(self.L.hb_halo_exchange(C.byref(self.desc), self.hb.stream_ptr(stream)), "hb_halo_exchange")
 
+    @staticmethod
+    def exchange_batch(halos, stream=None):
+        """several strip buffers in ONE launch (hb_halo_exchange_batch, one CTA per buffer)"""
+        import ctypes as C
+        live = [h for h in halos if h.desc is not None]
+        if not live:
+            return
+        arr = (C.POINTER(A.hb_halo_desc) * len(live))(*[C.pointer(h.desc) for h in live])
+        live[0].hb._check(live[0].L.hb_halo_exchange_batch(arr, len(live), live[0].hb.stream_ptr(stream)), "hb_halo_exchange_batch")
+
     def status(self):
         """(exchanges completed, timed_out flag) read back from the control block (synchronising)"""
         import ctypes as C
@@ -188,6 +198,22 @@ class P2PHalo:
         n, t = C.c_int(), C.c_int()
         self.hb._check(self.L.hb_halo_status(self.ctrl, C.byref(n), C.byref(t)), "hb_halo_status")
         return n.value, t.value
+
+
+def allgather_minmaxsum(partials, group=None):
+    """Combine the per-rank device partials of hb_reduce_minmaxsum_f32_async ({float min, float max, double sum} =
+    16 bytes, passed as a float32[4] CUDA tensor) with ONE collective: all-gather the 16-byte records, fold locally in
+    rank order (deterministic).  Returns a float64[3] CUDA tensor (min, max, sum); no host synchronisation."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        allp = partials.view(1, 4)
+    else:
+        allp = torch.empty((world, 4), dtype=torch.float32, device=partials.device)
+        dist.all_gather_into_tensor(allp, partials.view(1, 4), group=group)
+    sums = allp[:, 2:4].contiguous().view(torch.float64)
+    return torch.stack([allp[:, 0].min().double(), allp[:, 1].max().double(), sums.sum()])
 
 
 def allreduce_minmaxsum(mn, mx, sm, group=None, device=None):
@@ -292,6 +318,9 @@ def pyramid_traverse_strips(hb, pg, pl, mask, stream=None, group=None):
         pg.exchange(l - 1, stream, group)
         pyramid_down_step(hb, pg, pl, l, mask, stream)
     for l in range(pg.depth - 2, -1, -1):
-        pg.exchange(l + 1, stream, group)
-        pl.exchange(l + 1, stream, group)
+        if pg.halos is not None and pl.halos is not None:
+            P2PHalo.exchange_batch([pg.halos[l + 1], pl.halos[l + 1]], stream)   # both planes in one launch
+        else:
+            pg.exchange(l + 1, stream, group)
+            pl.exchange(l + 1, stream, group)
         pyramid_up_step(hb, pg, pl, l, stream)

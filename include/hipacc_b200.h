@@ -334,6 +334,9 @@ typedef struct {
   int down_ghost_top;        /* my rows land at row down_ghost_top - radius */
 } hb_halo_desc;
 int hb_halo_exchange(const hb_halo_desc *desc, void *stream);
+/* up to 4 strip buffers exchanged concurrently by one launch (one CTA each), e.g. the Gaussian and the
+ * Laplacian level before a pyramid up-transition */
+int hb_halo_exchange_batch(const hb_halo_desc *const *descs, int n, void *stream);
 
 #ifdef __cplusplus
 }

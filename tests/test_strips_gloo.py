@@ -34,6 +34,13 @@ def _worker(rank, world, port, boundary, radius, H, W, q):
         strips.exchange_halos(buf, plan)
         mn, mx, sm = strips.allreduce_minmaxsum(float(strips.owned(buf, plan)[:, :W].min()), float(strips.owned(buf, plan)[:, :W].max()),
                                                 float(strips.owned(buf, plan)[:, :W].double().sum()))
+        # the single-collective combine of the device partial records {float min, float max, double sum}
+        own = strips.owned(buf, plan)[:, :W]
+        rec = torch.zeros(4, dtype=torch.float32)
+        rec[0], rec[1] = own.min(), own.max()
+        rec[2:4].view(torch.float64)[0] = own.double().sum()
+        g3 = strips.allgather_minmaxsum(rec)
+        assert float(g3[0]) == mn and float(g3[1]) == mx and abs(float(g3[2]) - sm) <= 1e-12 * abs(sm)
         q.put((rank, plan.y0, plan.y1, plan.ghost_top, plan.ghost_bottom, buf[:, :W].numpy().copy(), (mn, mx, sm)))
     finally:
         dist.destroy_process_group()
