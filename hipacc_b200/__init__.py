@@ -54,6 +54,8 @@ def lib():
         L.hb_image_wrap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(A.hb_view)]
         L.hb_image_write.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
         L.hb_image_read.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
+        L.hb_image_write_region_async.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_size_t, C.c_void_p]
+        L.hb_image_read_region_async.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_size_t, C.c_void_p]
         L.hb_image_copy.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_image_copy_region.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_stream_synchronize.argtypes = [C.c_void_p]

@@ -224,6 +224,24 @@ int hb_image_read(const hb_view *img, void *host, void *stream) {
     return check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize()");
 }
 
+static int region_copy_async(const hb_view *v_, void *host, size_t host_pitch, bool to_device, void *stream, const char *who) {
+    HB_REQUIRE(v_ && v_->data && host, HB_ERR_INVALID, "%s: bad arguments", who);
+    hb_view v = norm_view(*v_);
+    HB_REQUIRE(view_ok(v), HB_ERR_INVALID, "%s: malformed view", who);
+    const size_t es = dtype_size(v.dtype), row = (size_t)v.width * es;
+    HB_REQUIRE(host_pitch >= row, HB_ERR_INVALID, "%s: host pitch smaller than a region row", who);
+    char *d = (char *)v.data + ((size_t)v.offset_y * v.stride + v.offset_x) * es;
+    const cudaError_t e = to_device ? cudaMemcpy2DAsync(d, (size_t)v.stride * es, host, host_pitch, row, v.height, cudaMemcpyHostToDevice, (cudaStream_t)stream)
+                                    : cudaMemcpy2DAsync(host, host_pitch, d, (size_t)v.stride * es, row, v.height, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return check_cuda(e, who);
+}
+int hb_image_write_region_async(const hb_view *region, const void *host, size_t host_pitch_bytes, void *stream) {
+    return region_copy_async(region, const_cast<void *>(host), host_pitch_bytes, true, stream, "hb_image_write_region_async");
+}
+int hb_image_read_region_async(const hb_view *region, void *host, size_t host_pitch_bytes, void *stream) {
+    return region_copy_async(region, host, host_pitch_bytes, false, stream, "hb_image_read_region_async");
+}
+
 int hb_image_copy(const hb_view *src, const hb_view *dst, void *stream) {
     HB_REQUIRE(src && dst && src->data && dst->data, HB_ERR_INVALID, "hb_image_copy: bad arguments");
     HB_REQUIRE(src->img_width == dst->img_width && src->img_height == dst->img_height && src->dtype == dst->dtype, HB_ERR_INVALID,

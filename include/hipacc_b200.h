@@ -107,6 +107,12 @@ int hb_image_wrap(void *device_ptr, int dtype, int width, int height, int stride
  * copies between a dense host array (stride == width) and the image. */
 int hb_image_write(const hb_view *img, const void *host, void *stream);
 int hb_image_read(const hb_view *img, void *host, void *stream);
+/* Asynchronous region transfers (an addition: the reference's hipaccWriteMemory / hipaccReadMemory block).  Copy the
+ * view's REGION (width x height at its offsets) from / to a host array whose rows are `host_pitch_bytes` apart; `host`
+ * points at the region's first pixel.  Enqueued on `stream` without synchronising: with pinned host memory the
+ * transfers of one row strip overlap the operators of another, and host->device overlaps device->host. */
+int hb_image_write_region_async(const hb_view *region, const void *host, size_t host_pitch_bytes, void *stream);
+int hb_image_read_region_async(const hb_view *region, void *host, size_t host_pitch_bytes, void *stream);
 /* hipaccCopyMemory / hipaccCopyMemoryRegion (runtime/hipacc_cu_standalone.hpp:166-216) */
 int hb_image_copy(const hb_view *src, const hb_view *dst, void *stream);
 int hb_image_copy_region(const hb_view *src, const hb_view *dst, void *stream);
