@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(HBX *HBY) harris_fused_kernel(const __grid_con
 // Version 2 of the fused kernel: the same arithmetic on the integer dot-product instructions.
 //   stage A  input tile as BYTES (5 KB instead of 20 KB), CLAMP applied by the loader;
 //   stage B  per intermediate position  dx*6 and dy*6 are five IDP.4A (dp4a.u32.s32) on byte windows of the three
-//            input rows -- the 3x3 Sobel sums fold into the accumulator operand, no adds; |d|/6 = umulhi(|d|, 10923<<16)
-//            (exact for |d| <= 765); products stored as packed 16-bit pairs (sxx, syy unsigned, sxy signed);
+//            input rows -- the 3x3 Sobel sums fold into the accumulator operand, no adds; d/6 by multiply-high
+//            (the compiler's multiply-high); products stored as packed 16-bit pairs (sxx, syy unsigned, sxy signed);
 //            each thread owns 4 adjacent positions x 5 rows and slides the byte windows down the rows;
 //   fix-up   (border tiles only) intermediates outside the image take the value at the CLAMPED position;
 //   stage C  3x3 binomial of the three planes = six IDP.2A (dp2a) per pixel and plane on 16-bit pairs: the
@@ -158,6 +158,11 @@ constexpr int H2_NT = 256;
 __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned mad_u32(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 __device__ __forceinline__ int dp2a_lo_uu(unsigned a, unsigned b, int c) {
@@ -196,10 +201,25 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
         const bool interior = x_start >= p.win.lo_x && x_start + 136 <= p.win.hi_x && y_start >= p.win.lo_y && y_start + 36 <= p.win.hi_y;
         const bool aligned = ((reinterpret_cast<uintptr_t>(p.in) + (size_t)x_start) % 4 == 0) && (p.in_stride % 4 == 0);
         if (interior && aligned) {
+            // all of a thread's loads are in flight before its first shared-memory store
             const uchar *base = p.in + (size_t)y_start * p.in_stride + x_start;
-            for (int v = tid; v < 36 * 34; v += H2_NT) {
-                const int r = v / 34, w = v - r * 34;
-                *reinterpret_cast<unsigned *>(tin + r * H2_TIN_STRIDE + 4 + 4 * w) = __ldg(reinterpret_cast<const unsigned *>(base + (size_t)r * p.in_stride) + w);
+            constexpr int NV = 36 * 34, PER = (NV + H2_NT - 1) / H2_NT;
+            unsigned t[PER];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int v = tid + k * H2_NT;
+                if (v < NV) {
+                    const int r = v / 34, w = v - r * 34;
+                    t[k] = __ldg(reinterpret_cast<const unsigned *>(base + (size_t)r * p.in_stride) + w);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int v = tid + k * H2_NT;
+                if (v < NV) {
+                    const int r = v / 34, w = v - r * 34;
+                    *reinterpret_cast<unsigned *>(tin + r * H2_TIN_STRIDE + 4 + 4 * w) = t[k];
+                }
             }
         } else {
             ImgRef<uchar> im{p.in, p.in_stride, p.in_iw, p.in_ih};
@@ -227,15 +247,15 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
                 for (int i = 0; i < 4; ++i) {
                     const int dx6 = dp4a_us(cur[i], 0x000100FF, dp4a_us(win[1][i], 0x000100FF, dp4a_us(win[0][i], 0x000100FF, 0)));
                     const int dy6 = dp4a_us(cur[i], 0x00010101, dp4a_us(win[0][i], 0x00FFFFFF, 0));
-                    const unsigned qx = __umulhi((unsigned)abs(dx6), 10923u << 16), qy = __umulhi((unsigned)abs(dy6), 10923u << 16);  // |d| / 6
-                    const int sg = (dx6 ^ dy6) >> 31;
-                    pxx[i] = qx * qx;
-                    pyy[i] = qy * qy;
-                    pxy[i] = (unsigned)(((int)(qx * qy) ^ sg) - sg);   // (dx/6) * (dy/6), C truncating division
+                    const int qx = dx6 / 6, qy = dy6 / 6;   // C truncating division (multiply-high by the compiler)
+                    pxx[i] = (unsigned)(qx * qx);
+                    pyy[i] = (unsigned)(qy * qy);
+                    pxy[i] = (unsigned)(qx * qy);
                 }
                 const int o = q * H2_PL_COLS + 4 * g;
-                *reinterpret_cast<uint2 *>(sxx + o) = make_uint2(pxx[0] | (pxx[1] << 16), pxx[2] | (pxx[3] << 16));
-                *reinterpret_cast<uint2 *>(syy + o) = make_uint2(pyy[0] | (pyy[1] << 16), pyy[2] | (pyy[3] << 16));
+                // pack with IMAD (FMA pipe) rather than shift + or (ALU pipe, the busier one in this kernel)
+                *reinterpret_cast<uint2 *>(sxx + o) = make_uint2(mad_u32(pxx[1], 65536u, pxx[0]), mad_u32(pxx[3], 65536u, pxx[2]));
+                *reinterpret_cast<uint2 *>(syy + o) = make_uint2(mad_u32(pyy[1], 65536u, pyy[0]), mad_u32(pyy[3], 65536u, pyy[2]));
                 *reinterpret_cast<uint2 *>(sxy + o) = make_uint2(__byte_perm(pxy[0], pxy[1], 0x5410), __byte_perm(pxy[2], pxy[3], 0x5410));
             }
 #pragma unroll
