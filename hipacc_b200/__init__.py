@@ -59,6 +59,10 @@ def lib():
         L.hb_image_copy.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_image_copy_region.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_stream_synchronize.argtypes = [C.c_void_p]
+        L.hb_graph_begin.argtypes = [C.c_void_p]
+        L.hb_graph_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.hb_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
+        L.hb_graph_destroy.argtypes = [C.c_void_p]
         L.hb_ipc_export.argtypes = [C.c_void_p, C.POINTER(A.hb_ipc_mem)]
         L.hb_ipc_open.argtypes = [C.POINTER(A.hb_ipc_mem), C.POINTER(C.c_void_p)]
         L.hb_ipc_close.argtypes = [C.c_void_p]
@@ -136,6 +140,32 @@ def empty_image(dtype, width, height, device="cuda", align_bytes=256):
     stride = (width + per - 1) // per * per
     buf = torch.empty((height, stride), dtype=torch_dtype(dtype), device=device)
     return buf[:, :width]
+
+
+class Graph:
+    """A captured pipeline (hb_graph_begin / hb_graph_end): `with hb.Graph(stream) as g: ...operators on stream...`,
+    then g.launch() replays every kernel of the block with one launch (the reference's -use-graph mode)."""
+
+    def __init__(self, stream):
+        self.stream, self.handle = stream, C.c_void_p()
+
+    def __enter__(self):
+        _check(lib().hb_graph_begin(stream_ptr(self.stream)), "hb_graph_begin")
+        return self
+
+    def __exit__(self, et, ev, tb):
+        rc = lib().hb_graph_end(stream_ptr(self.stream), C.byref(self.handle))
+        if et is None:
+            _check(rc, "hb_graph_end")
+        return False
+
+    def launch(self, stream=None):
+        _check(lib().hb_graph_launch(self.handle, stream_ptr(self.stream if stream is None else stream)), "hb_graph_launch")
+
+    def destroy(self):
+        if self.handle:
+            lib().hb_graph_destroy(self.handle)
+            self.handle = C.c_void_p()
 
 
 class _DevArray:

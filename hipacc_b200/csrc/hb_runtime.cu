@@ -242,6 +242,31 @@ int hb_image_read_region_async(const hb_view *region, void *host, size_t host_pi
     return region_copy_async(region, host, host_pitch_bytes, false, stream, "hb_image_read_region_async");
 }
 
+int hb_graph_begin(void *stream) {
+    HB_REQUIRE(stream, HB_ERR_INVALID, "hb_graph_begin: capture needs a non-default stream");
+    return check_cuda(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture()");
+}
+int hb_graph_end(void *stream, hb_graph **out) {
+    HB_REQUIRE(stream && out, HB_ERR_INVALID, "hb_graph_end: null argument");
+    cudaGraph_t g = nullptr;
+    int rc = check_cuda(cudaStreamEndCapture((cudaStream_t)stream, &g), "cudaStreamEndCapture()");
+    if (rc) return rc;
+    cudaGraphExec_t ex = nullptr;
+    rc = check_cuda(cudaGraphInstantiate(&ex, g, 0), "cudaGraphInstantiate()");
+    cudaGraphDestroy(g);
+    if (rc) return rc;
+    *out = reinterpret_cast<hb_graph *>(ex);
+    return HB_OK;
+}
+int hb_graph_launch(hb_graph *g, void *stream) {
+    HB_REQUIRE(g, HB_ERR_INVALID, "hb_graph_launch: null graph");
+    return check_cuda(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(g), (cudaStream_t)stream), "cudaGraphLaunch()");
+}
+int hb_graph_destroy(hb_graph *g) {
+    if (!g) return HB_OK;
+    return check_cuda(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(g)), "cudaGraphExecDestroy()");
+}
+
 int hb_image_copy(const hb_view *src, const hb_view *dst, void *stream) {
     HB_REQUIRE(src && dst && src->data && dst->data, HB_ERR_INVALID, "hb_image_copy: bad arguments");
     HB_REQUIRE(src->img_width == dst->img_width && src->img_height == dst->img_height && src->dtype == dst->dtype, HB_ERR_INVALID,

@@ -126,6 +126,22 @@ float hb_last_kernel_ms(void);
 long long hb_launch_count(void);
 int hb_stream_synchronize(void *stream);
 
+/* ------------------------------------------------------------------ CUDA graphs */
+/*
+ * The reference's -use-graph mode builds a cudaGraph node by node (hipaccLaunchKernelCudaGraph,
+ * hipaccWriteMemoryCudaGraph, runtime/hipacc_cu_standalone.hpp:331-356, hipacc_cu.hpp:260-285).  Here
+ * every non-blocking entry point of this library (operators, hb_halo_exchange, hb_*_async, the
+ * region copies) is capturable: bracket a pipeline with hb_graph_begin / hb_graph_end on a
+ * non-default stream and replay it with hb_graph_launch -- one launch for a multi-kernel program
+ * (the unfused Harris pipeline: 9 kernels; a pyramid traversal: 14), no per-kernel host cost.
+ * Blocking calls (hb_reduce, hb_binning, hb_image_write / read) must stay outside a capture.
+ */
+typedef struct hb_graph hb_graph;
+int hb_graph_begin(void *stream);
+int hb_graph_end(void *stream, hb_graph **out);
+int hb_graph_launch(hb_graph *g, void *stream);
+int hb_graph_destroy(hb_graph *g);
+
 /* ------------------------------------------------------------------ local operators */
 /*
  * Replaces one generated local-operator kernel + its launch (kernel text

@@ -320,6 +320,47 @@ def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
             np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
 
 
+# ------------------------------------------------------------------ CUDA graphs (the reference's -use-graph mode)
+def test_graph_replay_of_multi_kernel_pipelines(hb, oracle, dev):
+    """hb_graph_begin / hb_graph_end capture the nine kernels of the unfused Harris pipeline and a pyramid traversal;
+    replays on fresh inputs equal the oracle (no per-kernel host work between the kernels)."""
+    import torch
+    stream = torch.cuda.Stream(device=dev)
+    img0, img1 = synth.blocks_np(640, 333, seed=5), synth.blocks_np(640, 333, seed=6)
+    src = to_dev(hb, img0, dev)
+    with torch.cuda.stream(stream):
+        hb.harris_unfused(src, stream=stream)          # warm-up outside the capture (lazy kernel loading)
+        stream.synchronize()
+        n0 = hb.launch_count()
+        with hb.Graph(stream) as g:
+            out = hb.harris_unfused(src, stream=stream)[0]
+        assert hb.launch_count() - n0 == 9
+        for img in (img1, img0):
+            src.copy_(torch.from_numpy(img).to(dev))
+            stream.synchronize()
+            g.launch()
+            stream.synchronize()
+            np.testing.assert_array_equal(to_np(out), oracle.harris(img))
+        g.destroy()
+        f0 = synth.image_np("float32", 256, 192, seed=31)
+        pg = hb.Pyramid(to_dev(hb, f0, dev), 4)
+        pl = hb.Pyramid(torch.zeros_like(pg.levels[0]), 4)
+        hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream)
+        stream.synchronize()
+        with hb.Graph(stream) as g2:
+            hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream)
+        f1 = synth.image_np("float32", 256, 192, seed=32)
+        pg.levels[0].copy_(torch.from_numpy(f1).to(dev))
+        stream.synchronize()
+        g2.launch()
+        stream.synchronize()
+        og, ol = oracle.pyramid(f1, 4, M.GAUSS5)
+        for lv in range(4):
+            np.testing.assert_array_equal(to_np(pg.levels[lv]), og[lv])
+            np.testing.assert_array_equal(to_np(pl.levels[lv]), ol[lv])
+        g2.destroy()
+
+
 # ------------------------------------------------------------------ vector pixel types (uchar4)
 @pytest.mark.parametrize("b", [A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT])
 def test_rgba_local_ops_vs_golden(hb, dev, b):
