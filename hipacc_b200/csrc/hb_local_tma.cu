@@ -72,7 +72,7 @@ struct Geo {
 // One CTA: NST shared-memory stages, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the box of tile j + NST - 1
 // is requested before tile j is computed.
 template <int SX, int SY, typename MASK, int RPT, int BY, int NST>
-__global__ void __launch_bounds__(32 * BY) local_tma_f32_kernel(const __grid_constant__ LocalParams p,
+__global__ void __launch_bounds__(32 * BY, NST == 1 ? 8 : 1) local_tma_f32_kernel(const __grid_constant__ LocalParams p,
                                                                 const __grid_constant__ CUtensorMap tmap, const int ntx,
                                                                 const int ntiles, const int stream_stores) {
     typedef Geo<SX, SY, RPT, BY, NST> G;
