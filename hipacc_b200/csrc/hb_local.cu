@@ -17,6 +17,7 @@
 //     unrolled for 3x3 / 5x5 / 7x7; other sizes use the generic kernel below.
 #include "hb_local.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace hb {
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
                                                (TI)cval_of<TS>(p), p.in_ox + gx0 - HXP, p.in_oy + gy0 - HY, tid);
     __syncthreads();
 
-    const int mode = VAR == 0 ? (int)HB_REDUCE_SUM : p.reduce_mode;
+    const int mode = VAR != 1 ? (int)HB_REDUCE_SUM : p.reduce_mode;
     TS acc[RPT][4];
 #pragma unroll
     for (int r = 0; r < RPT; ++r)
@@ -63,6 +64,25 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
             TS t[4];
             load4(row + 4 * q, t);
             w[4 * q] = t[0]; w[4 * q + 1] = t[1]; w[4 * q + 2] = t[2]; w[4 * q + 3] = t[3];
+        }
+        if (VAR == 2) {
+            // separable integer mask m = v * h^T (p.coef.i[0..SX) = h, [SX..SX+SY) = v): horizontal pass once per staged
+            // row, vertical weights per output row.  Integer sums are exact in any order, so this equals the 2-D fold.
+            TS h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                h[i] = 0;
+#pragma unroll
+                for (int dx = 0; dx < SX; ++dx) h[i] = add_rn(h[i], mul_rn(coef_of<TS>(p, dx), w[HXP - HX + i + dx * CH]));
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int dy = ir - r;
+                if (dy < 0 || dy >= SY) continue;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r][i] = add_rn(acc[r][i], mul_rn(coef_of<TS>(p, SX + dy), h[i]));
+            }
+            continue;
         }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
@@ -163,6 +183,44 @@ static int launch_local_x4(const LocalParams &p, bool fast, cudaStream_t s) {
     return HB_ERR_UNSUPPORTED;
 }
 
+// register-blocked two-pass variant for separable INTEGER masks (VAR 2); p.coef.i holds h then v
+template <typename TI, typename TO>
+static int launch_local_separable(const LocalParams &p, cudaStream_t s) {
+    dim3 block(BX, BY);
+    dim3 grid((p.is_w + TW - 1) / TW, (p.is_h + TH - 1) / TH);
+#define HB_SEP(SXV, SYV)                                                          \
+    if (p.size_x == SXV && p.size_y == SYV) {                                     \
+        local_tiled_kernel<TI, int, TO, SXV, SYV, 2><<<grid, block, 0, s>>>(p);   \
+        g_launches++;                                                             \
+        return HB_OK;                                                             \
+    }
+    HB_SEP(3, 3)
+    HB_SEP(5, 5)
+    HB_SEP(7, 7)
+#undef HB_SEP
+    return HB_ERR_UNSUPPORTED;
+}
+
+// m[j][i] == v[j] * h[i] with integer h, v?  (rank-1 factorisation through the first non-zero entry)
+static bool factor_separable(const int *m, int sx, int sy, int *h, int *v) {
+    int r0 = -1, c0 = -1;
+    for (int k = 0; k < sx * sy && r0 < 0; ++k)
+        if (m[k]) { r0 = k / sx; c0 = k % sx; }
+    if (r0 < 0) return false;
+    auto gcd = [](long long a, long long b) { a = a < 0 ? -a : a; b = b < 0 ? -b : b; while (b) { long long t = a % b; a = b; b = t; } return a; };
+    long long g = 0;
+    for (int i = 0; i < sx; ++i) g = gcd(g, m[r0 * sx + i]);
+    for (int i = 0; i < sx; ++i) h[i] = (int)(m[r0 * sx + i] / g);
+    for (int j = 0; j < sy; ++j) {
+        if (m[j * sx + c0] % h[c0]) return false;
+        v[j] = m[j * sx + c0] / h[c0];
+    }
+    for (int j = 0; j < sy; ++j)
+        for (int i = 0; i < sx; ++i)
+            if ((long long)v[j] * h[i] != m[j * sx + i]) return false;
+    return true;
+}
+
 template <typename TI, typename TS, typename TO>
 static int launch_local(const LocalParams &p, bool fast, cudaStream_t s) {
     dim3 block(BX, BY);
@@ -255,10 +313,26 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
         }
         else if (it == HB_S8 && ot == HB_S8) rc = launch_local<signed char, float, signed char>(p, fast, s);
     } else {
-        if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, int, uchar>(p, fast, s);
-        else if (it == HB_U8 && ot == HB_S32) rc = launch_local<uchar, int, int>(p, fast, s);
-        else if (it == HB_U8 && ot == HB_S16) rc = launch_local<uchar, int, short>(p, fast, s);
-        else if (it == HB_S16 && ot == HB_S16) rc = launch_local<short, int, short>(p, fast, s);
+        // separable integer masks (Sobel 3x3 / 5x5 / 7x7, binomial Gaussians): two-pass variant, SX + SY instead of
+        // SX * SY multiply-adds per pixel; exact because integer sums do not depend on the order
+        static int no_sep = -1;
+        if (no_sep < 0) { const char *e = getenv("HB_NO_SEPARABLE"); no_sep = (e && atoi(e)) ? 1 : 0; }
+        int hv[2 * 13];
+        if (fast && !no_sep && p.size_x == p.size_y && p.size_x <= 7 && p.size_x >= 3 &&
+            factor_separable(p.coef.i, p.size_x, p.size_y, hv, hv + p.size_x)) {
+            LocalParams q = p;
+            for (int k = 0; k < p.size_x + p.size_y; ++k) q.coef.i[k] = hv[k];
+            if (it == HB_U8 && ot == HB_U8) rc = launch_local_separable<uchar, uchar>(q, s);
+            else if (it == HB_U8 && ot == HB_S32) rc = launch_local_separable<uchar, int>(q, s);
+            else if (it == HB_U8 && ot == HB_S16) rc = launch_local_separable<uchar, short>(q, s);
+            else if (it == HB_S16 && ot == HB_S16) rc = launch_local_separable<short, short>(q, s);
+        }
+        if (rc == HB_ERR_UNSUPPORTED) {
+            if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, int, uchar>(p, fast, s);
+            else if (it == HB_U8 && ot == HB_S32) rc = launch_local<uchar, int, int>(p, fast, s);
+            else if (it == HB_U8 && ot == HB_S16) rc = launch_local<uchar, int, short>(p, fast, s);
+            else if (it == HB_S16 && ot == HB_S16) rc = launch_local<short, int, short>(p, fast, s);
+        }
     }
     HB_REQUIRE(rc != HB_ERR_UNSUPPORTED, HB_ERR_UNSUPPORTED,
                "hb_local_op: no device kernel for (in %d, acc %d, out %d); there is no CPU fallback", it, d->acc_dtype, ot);
