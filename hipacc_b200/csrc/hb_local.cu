@@ -65,6 +65,43 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
             load4(row + 4 * q, t);
             w[4 * q] = t[0]; w[4 * q + 1] = t[1]; w[4 * q + 2] = t[2]; w[4 * q + 3] = t[3];
         }
+        if (VAR == 0 && sizeof(TS) == 4 && DtypeOf<TS>::v == HB_F32 && SX <= 7 && SY <= 7) {
+            // float SUM of products with packed multiplies; per accumulator the products are still added one by one in
+            // tap order (row-major), so the result is bit-identical to the scalar form
+            float(&wf)[WIN] = reinterpret_cast<float(&)[WIN]>(w);
+            float(&af)[RPT][4] = reinterpret_cast<float(&)[RPT][4]>(acc);
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int dy = ir - r;
+                if (dy < 0 || dy >= SY) continue;
+                if (CH == 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        constexpr int base = HXP - HX;
+                        const int odd = (base + i) & 1;   // compile-time after unrolling: first tap in an odd register
+                        if (odd) af[r][i] = __fadd_rn(af[r][i], __fmul_rn(p.coef.f[dy * SX], wf[base + i]));
+#pragma unroll
+                        for (int dx = odd; dx + 1 < SX; dx += 2) {
+                            float p0, p1;
+                            mul2_rn(wf[base + i + dx], wf[base + i + dx + 1], &p.cpair[odd][dy][dx - odd], p0, p1);
+                            af[r][i] = __fadd_rn(__fadd_rn(af[r][i], p0), p1);
+                        }
+                        if (((SX - odd) & 1) != 0) af[r][i] = __fadd_rn(af[r][i], __fmul_rn(p.coef.f[dy * SX + SX - 1], wf[base + i + SX - 1]));
+                    }
+                } else {
+#pragma unroll
+                    for (int dx = 0; dx < SX; ++dx)
+#pragma unroll
+                        for (int i = 0; i < 4; i += 2) {   // two adjacent channel elements share the coefficient
+                            float p0, p1;
+                            mul2_rn(wf[HXP - HX + i + dx * CH], wf[HXP - HX + i + 1 + dx * CH], p.cdup[dy * SX + dx], p0, p1);
+                            af[r][i] = __fadd_rn(af[r][i], p0);
+                            af[r][i + 1] = __fadd_rn(af[r][i + 1], p1);
+                        }
+                }
+            }
+            continue;
+        }
         if (VAR == 2) {
             // separable integer mask m = v * h^T (p.coef.i[0..SX) = h, [SX..SX+SY) = v): horizontal pass once per staged
             // row, vertical weights per output row.  Integer sums are exact in any order, so this equals the 2-D fold.
@@ -295,6 +332,14 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
         }
     }
     HB_REQUIRE(visited > 0, HB_ERR_INVALID, "hb_local_op: empty domain");
+    if (facc && d->tap == HB_TAP_MUL && d->size_x <= 7 && d->size_y <= 7) {   // operands of the packed multiplies
+        for (int dy = 0; dy < d->size_y; ++dy)
+            for (int dx = 0; dx < 8; ++dx) {
+                p.cpair[0][dy][dx] = dx < d->size_x ? p.coef.f[dy * d->size_x + dx] : 0.0f;
+                p.cpair[1][dy][dx] = dx + 1 < d->size_x ? p.coef.f[dy * d->size_x + dx + 1] : 0.0f;
+            }
+        for (int k = 0; k < n; ++k) p.cdup[k][0] = p.cdup[k][1] = p.coef.f[k];
+    }
     const bool fast = d->reduce_mode == HB_REDUCE_SUM && d->tap == HB_TAP_MUL;
 
     cudaStream_t s = (cudaStream_t)stream;

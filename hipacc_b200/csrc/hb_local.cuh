@@ -26,6 +26,13 @@ struct LocalParams {
         float f[kMaxTaps];
         int i[kMaxTaps];
     } coef;
+    // packed-FP32 multiply (FMUL2, sm_100a) operands for the float SUM-of-products path of masks up to 7 x 7, rows
+    // padded to 8 floats so that every pair is 8-byte aligned in the constant bank:
+    //   cpair[0][dy][dx] = c[dy][dx]      -> pairs (c0,c1) (c2,c3) ...   for pixels whose first tap sits in an even register
+    //   cpair[1][dy][dx] = c[dy][dx + 1]  -> pairs (c1,c2) (c3,c4) ...   for the others
+    //   cdup[k]          = (c[k], c[k])   -> one coefficient for two adjacent channel elements (uchar4 images)
+    float cpair[2][7][8];
+    float cdup[49][2];
 };
 
 // ---- arithmetic in the accumulation type (float: separately rounded mul / add) ----
@@ -49,6 +56,16 @@ __device__ __forceinline__ TS fold(TS acc, TS v, int mode) {
     case HB_REDUCE_MAX: return v > acc ? v : acc;
     default: return mul_rn(acc, v);
     }
+}
+
+// two separately rounded products in one instruction: (a.lo * b.lo, a.hi * b.hi).  FMUL2 issues at the scalar FMUL
+// rate (profiles/r1h_fp32x2_probe.txt).  The additions stay scalar FADDs: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2 even with --fmad=false, which would break the separately-rounded contract.
+__device__ __forceinline__ void mul2_rn(float a0, float a1, const float *b_pair, float &p0, float &p1) {
+    unsigned long long a, b = *reinterpret_cast<const unsigned long long *>(b_pair), r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(r));
 }
 
 template <typename TS> __device__ __forceinline__ TS coef_of(const LocalParams &p, int k);
