@@ -4,7 +4,7 @@
 // (runtime/hipacc_cu.tpp:410-464, runtime/hipacc_cu_red.hpp:527-641: per-warp hand-rolled locks in
 // shared memory, a second merge kernel, cudaMalloc/cudaFree per call).
 //
-// One pass over HBM (4 B per float pixel, 1 B per uchar pixel): a persistent grid walks row chunks with
+// One pass over HBM (4 B per float pixel, 1 B per uchar pixel): 16 CTAs per SM walk the row chunks with
 // 16-byte streaming loads (4 independent loads in flight per thread); every warp owns a private copy of
 // the bins in shared memory (native shared-memory atomics, no cross-warp contention); at the end the
 // CTA folds its copies and adds the non-zero bins to the result with global atomics.  Integer addition

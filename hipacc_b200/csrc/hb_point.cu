@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) point_kernel(const __grid_constant__ Poin
     }
 }
 
-// Streaming path (no interpolation, 4-pixel aligned rows): a persistent grid walks row chunks of PT x PU
+// Streaming path (no interpolation, 4-pixel aligned rows): one CTA per row chunk of PT x PU
 // 4-pixel vectors; every thread first issues its PU independent vector loads per input (PU x NIN x 16 bytes
 // in flight for float), then evaluates and stores.  OP and NIN are compile-time so the body is straight-line.
 constexpr int PT = 256, PU = 4;

@@ -4,7 +4,7 @@
 // runtime/hipacc_cu_red.hpp:140-346: one pixel per thread, warp-synchronous shared-memory tree,
 // 3 cudaMalloc/cudaFree + a blocking memcpy per call).
 //
-// One pass over HBM: a persistent grid (a multiple of the SM count) strides over the rows with
+// One pass over HBM: 16 CTAs per SM stride over the row chunks with
 // 16-byte loads, each thread keeps private accumulators, then warp shuffles -> one partial per
 // CTA -> the last CTA to finish (atomic ticket) folds the partials in a FIXED order, so results are
 // deterministic for a given grid.  min, max and sum are produced by the same pass (fused).

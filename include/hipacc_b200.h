@@ -86,7 +86,7 @@ typedef struct {
  * drives (one process per GPU; the reference always picks device 0). */
 int hb_init(int device);
 int hb_device_count(void);
-/* number of SMs, used to size persistent grids */
+/* number of SMs of the selected device */
 int hb_sm_count(void);
 
 typedef void (*hb_log_fn)(int level /*0 info,1 warn,2 error*/, const char *msg);
