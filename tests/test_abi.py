@@ -60,6 +60,22 @@ def test_struct_layouts_match_the_compiler(tmp_path):
     assert got == want
 
 
+def test_new_struct_layouts_match_the_compiler(tmp_path):
+    """binning / halo / IPC descriptors: ctypes mirror vs the real header"""
+    import subprocess
+    src = tmp_path / "lay2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hipacc_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(hb_binning_desc), offsetof(hb_binning_desc, p0),'
+                   'sizeof(hb_halo_desc), offsetof(hb_halo_desc, ctrl), offsetof(hb_halo_desc, down_ghost_top), sizeof(hb_ipc_mem),'
+                   '(size_t)HB_U8X4);return 0;}\n')
+    exe = tmp_path / "lay2"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(A.hb_binning_desc), A.hb_binning_desc.p0.offset, C.sizeof(A.hb_halo_desc), A.hb_halo_desc.ctrl.offset,
+            A.hb_halo_desc.down_ghost_top.offset, C.sizeof(A.hb_ipc_mem), A.U8X4]
+    assert got == want
+
+
 def test_pyramid_sizes_truncate_like_the_reference():
     assert S.pyramid_sizes(16384, 16384, 8)[-1] == (128, 128)
     assert S.pyramid_sizes(101, 67, 3) == [(101, 67), (50, 33), (25, 16)]
