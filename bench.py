@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning sweeps only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N > 1: halo exchange by peer-to-peer push kernel (default) or NCCL send/recv")
     ap.add_argument("--e2e-blocking", action="store_true", help="time the end-to-end leg with the blocking hb_image_write / hb_image_read calls (the reference's API shape) instead of the pipelined async region copies")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: run the halo kernel in stream order instead of overlapping it with the first operator's interior rows")
     ap.add_argument("--no-graph", action="store_true", help="launch every operator from the host instead of replaying a CUDA graph of one step")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -212,7 +213,30 @@ def main():
 
     skip_exchange = bool(int(os.environ.get("HB_BENCH_NO_EXCHANGE", "0")))   # diagnosis only: kernels without the halo exchange
 
+    # N > 1 with the peer-to-peer exchange: the halo kernel runs on a side stream while the first operator works on the
+    # rows that do not touch the ghost rows; its two 32-row edge strips and the other operators follow the join.
+    overlap = halo is not None and not args.no_overlap and plan.rows > 4 * 32
+    side = torch.cuda.Stream(device=dev) if overlap else None
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+    E = 32
+    gt_, gb_ = plan.ghost_top, plan.ghost_bottom
+    roi_mid, ghost_mid = (W, plan.rows - 2 * E, 0, gt_ + E), (gt_ + E, gb_ + E)
+    roi_top, ghost_top_ = (W, E, 0, gt_), (gt_, plan.rows - E + gb_)
+    roi_bot, ghost_bot = (W, E, 0, gt_ + plan.rows - E), (gt_ + plan.rows - E, gb_)
+
     def step_direct():
+        if overlap and not skip_exchange:
+            ev_fork.record(stream)
+            side.wait_event(ev_fork)
+            halo.exchange(side)
+            ev_join.record(side)
+            hb.local_op(specs[0], src, dst=outs[0], roi_in=roi_mid, roi_out=roi_mid, ghost=ghost_mid, stream=stream)
+            stream.wait_event(ev_join)
+            hb.local_op(specs[0], src, dst=outs[0], roi_in=roi_top, roi_out=roi_top, ghost=ghost_top_, stream=stream)
+            hb.local_op(specs[0], src, dst=outs[0], roi_in=roi_bot, roi_out=roi_bot, ghost=ghost_bot, stream=stream)
+            for s, o in zip(specs[1:], outs[1:]):
+                hb.local_op(s, src, dst=o, roi_in=roi, roi_out=roi, ghost=ghost, stream=stream)
+            return
         if skip_exchange:
             pass
         elif halo is not None:
@@ -226,7 +250,7 @@ def main():
     # replayed (the reference's own -use-graph mode, runtime/hipacc_cu_standalone.hpp:331-356), so the timed region
     # is not bounded by the Python host; at N > 1 the NCCL send/recv pair of the halo exchange is part of the graph.
     use_graph = not args.no_graph and not (world > 1 and halo is None)   # NCCL send/recv stays outside graphs
-    launches_per_step = len(OPS) + (1 if halo is not None else 0)
+    launches_per_step = len(OPS) + (1 if halo is not None else 0) + (2 if overlap else 0)
     step, graph_note = step_direct, "direct launches through hb_local_op"
     if use_graph:
         step_direct()            # also creates the NCCL P2P communicators before capture
@@ -246,7 +270,7 @@ def main():
         use_graph = bool(ok)
         if use_graph:
             step = graph.replay
-            graph_note = "CUDA graph replay of the step (3 operator kernels" + (" + 1 peer-to-peer halo kernel)" if world > 1 else ")")
+            graph_note = "CUDA graph replay of the step (3 operator kernels" + ((" + 1 peer-to-peer halo kernel" + (" overlapped with the first operator's interior rows, 2 edge-strip launches)" if overlap else ")")) if world > 1 else ")")
 
     def sync_all():
         torch.cuda.synchronize()
