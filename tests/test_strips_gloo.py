@@ -90,3 +90,20 @@ def test_plan_partitions_every_row_once():
         assert plans[0].ghost_top == 0 and plans[-1].ghost_bottom == 0
     with pytest.raises(AssertionError):
         strips.StripPlan(16, 8, 8, 0, 2).validate()
+
+
+def test_strip_pyramid_levels_align_across_ranks():
+    """every level is cut at the same relative rows: strip boundaries halve exactly from level to level, so a strip's
+    local row parity equals the global one (the condition the fused level kernels rely on)"""
+    for world, H, W, depth, R in [(2, 256, 392, 3, 4), (8, 16384, 16384, 8, 4), (4, 512, 264, 4, 3), (3, 384, 520, 3, 5)]:
+        pyrs = [strips.StripPyramid(W, H, depth, world, r, R, "cpu") for r in range(world)]
+        for l in range(depth):
+            plans = [p.plans[l] for p in pyrs]
+            assert plans[0].y0 == 0 and plans[-1].y1 == H >> l
+            assert all(plans[i].y1 == plans[i + 1].y0 for i in range(world - 1))
+            assert all(pl.y0 == pyrs[i].plans[0].y0 >> l and pl.rows == pyrs[i].plans[0].rows >> l for i, pl in enumerate(plans))
+            assert all(pl.rows % 2 == 0 or l == depth - 1 for pl in plans)
+            assert plans[0].ghost_top == 0 and plans[-1].ghost_bottom == 0 and all(pl.ghost_top == R for pl in plans[1:])
+            assert all(tuple(p.bufs[l].shape)[0] == p.plans[l].buffer_rows for p in pyrs)
+    with pytest.raises(AssertionError):
+        strips.StripPyramid(256, 100, 3, 2, 0, 4, "cpu")   # 100 rows cannot be cut into 2 strips of multiples of 4
