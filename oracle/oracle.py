@@ -363,6 +363,18 @@ def ref_laplace_rgba(img, mask, boundary):
     return out
 
 
+def ref_dilate_rgba(img, sx, sy, boundary):
+    out = np.zeros_like(img)
+    _check(ref_lib().ref_dilate_rgba(_p(img, C.c_ubyte), _p(out, C.c_ubyte), img.shape[1], img.shape[0], sx, sy, boundary), "ref_dilate_rgba")
+    return out
+
+
+def ref_box_rgba(img, sx, sy, boundary):
+    out = np.zeros_like(img)
+    _check(ref_lib().ref_box_rgba(_p(img, C.c_ubyte), _p(out, C.c_ubyte), img.shape[1], img.shape[0], sx, sy, boundary), "ref_box_rgba")
+    return out
+
+
 def ref_sample_histogram_f32(img, num_bins):
     """the Histogram sample's Kernel (binning() + binned_data()) executed by the reference DSL"""
     out = np.zeros(num_bins, dtype=np.uint32)

@@ -117,6 +117,22 @@ namespace smp_laplace_rgba {
 #undef WIDTH
 #undef HEIGHT
 #undef IMAGE
+namespace smp_dilate_rgba {
+#include "1_Local_Operators/Dilate_RGBA/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
+namespace smp_box_rgba {
+#include "1_Local_Operators/Box_Blur_RGBA/src/main.cpp"
+}
+#undef SIZE_X
+#undef SIZE_Y
+#undef WIDTH
+#undef HEIGHT
+#undef IMAGE
 namespace smp_hist {
 #include "2_Global_Operators/Histogram/src/main.cpp"
 }
@@ -719,6 +735,33 @@ int ref_laplace_rgba(const uchar *in, uchar *out, int w, int h, const int *coef,
     }
     DISPATCH_SIZE(size, size, CALL);
 #undef CALL
+    return 0;
+}
+
+// sample Dilate of Dilate_RGBA (src/main.cpp:48-64): reduce(dom, Reduce::MAX, in(dom)) on uchar4
+int ref_dilate_rgba(const uchar *in, uchar *out, int w, int h, int sx, int sy, int bmode) {
+    Image<uchar4> I(w, h, reinterpret_cast<uchar4 *>(const_cast<uchar *>(in)));
+    Image<uchar4> O(w, h);
+    Domain dom(sx, sy);
+    BoundaryCondition<uchar4> bc = make_bc(I, dom, bmode);
+    Accessor<uchar4> acc(bc);
+    IterationSpace<uchar4> is(O);
+    smp_dilate_rgba::Dilate k(is, acc, dom);
+    k.execute();
+    std::memcpy(out, O.data(), (size_t)4 * w * h);
+    return 0;
+}
+// sample BlurFilter of Box_Blur_RGBA (src/main.cpp:50-70): int4 sum over the Domain, convert_uchar4(float4(sum) / (sx*sy))
+int ref_box_rgba(const uchar *in, uchar *out, int w, int h, int sx, int sy, int bmode) {
+    Image<uchar4> I(w, h, reinterpret_cast<uchar4 *>(const_cast<uchar *>(in)));
+    Image<uchar4> O(w, h);
+    Domain dom(sx, sy);
+    BoundaryCondition<uchar4> bc = make_bc(I, dom, bmode);
+    Accessor<uchar4> acc(bc);
+    IterationSpace<uchar4> is(O);
+    smp_box_rgba::BlurFilter k(is, acc, dom, sx, sy);
+    k.execute();
+    std::memcpy(out, O.data(), (size_t)4 * w * h);
     return 0;
 }
 

@@ -95,6 +95,8 @@ def rgba():
             out[f"gauss_rgba_{sz}_{b}"] = O.ref_gaussian_rgba(img, M.GAUSS[sz], b)
         out[f"laplace_rgba_3_{b}"] = O.ref_laplace_rgba(img, M.LAPLACE3, b)
         out[f"laplace_rgba_5_{b}"] = O.ref_laplace_rgba(img, M.LAPLACE5, b)
+        out[f"dilate_rgba_3_{b}"] = O.ref_dilate_rgba(img, 3, 3, b)
+        out[f"box_rgba_5_{b}"] = O.ref_box_rgba(img, 5, 5, b)
     np.savez_compressed(os.path.join(HERE, "reference_rgba.npz"), **out)
     print("wrote", len(out), "arrays to reference_rgba.npz")
 

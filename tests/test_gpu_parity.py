@@ -371,6 +371,8 @@ def test_rgba_local_ops_vs_golden(hb, dev, b):
         np.testing.assert_array_equal(to_np(hb.local_op(S.gaussian_blur(M.GAUSS[sz], b), img)), g[f"gauss_rgba_{sz}_{b}"])
     np.testing.assert_array_equal(to_np(hb.local_op(S.laplace_u8(M.LAPLACE3, b, add=0), img)), g[f"laplace_rgba_3_{b}"])
     np.testing.assert_array_equal(to_np(hb.local_op(S.laplace_u8(M.LAPLACE5, b, add=0), img)), g[f"laplace_rgba_5_{b}"])
+    np.testing.assert_array_equal(to_np(hb.local_op(S.minmax_u8(3, 3, True, b), img)), g[f"dilate_rgba_3_{b}"])
+    np.testing.assert_array_equal(to_np(hb.local_op(S.box_blur_u8(5, 5, b), img)), g[f"box_rgba_5_{b}"])
 
 
 @pytest.mark.parametrize("shape", [(300, 517), (33, 40), (2, 3), (1, 1), (131, 1024)])

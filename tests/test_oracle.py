@@ -95,6 +95,8 @@ def test_rgba_vs_golden(oracle, b):
         np.testing.assert_array_equal(oracle.local_op_x4(S.gaussian_blur(M.GAUSS[sz], b), img), g[f"gauss_rgba_{sz}_{b}"])
     np.testing.assert_array_equal(oracle.local_op_x4(S.laplace_u8(M.LAPLACE3, b, add=0), img), g[f"laplace_rgba_3_{b}"])
     np.testing.assert_array_equal(oracle.local_op_x4(S.laplace_u8(M.LAPLACE5, b, add=0), img), g[f"laplace_rgba_5_{b}"])
+    np.testing.assert_array_equal(oracle.local_op_x4(S.minmax_u8(3, 3, True, b), img), g[f"dilate_rgba_3_{b}"])
+    np.testing.assert_array_equal(oracle.local_op_x4(S.box_blur_u8(5, 5, b), img), g[f"box_rgba_5_{b}"])
 
 
 def test_histogram_vs_golden(oracle):
