@@ -15,6 +15,7 @@
 #include "hb_common.cuh"
 #include "hb_internal.h"
 
+#include <cuda.h>   // CUdeviceptr / CUresult types only
 #include <cstring>
 
 namespace hb {
@@ -100,8 +101,35 @@ __global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_consta
 
 using namespace hb;
 
+// base address of the allocation that contains `p` (cuMemGetAddressRange, resolved through cudart: no -lcuda)
+static bool allocation_base(const void *p, const void **base) {
+    typedef CUresult (*Fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuMemGetAddressRange", &sym, 12000, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<Fn>(sym);
+        else
+            cudaGetLastError();
+    }
+    if (!fn) return false;
+    CUdeviceptr b = 0;
+    size_t sz = 0;
+    if (fn(&b, &sz, reinterpret_cast<CUdeviceptr>(p)) != CUDA_SUCCESS) return false;
+    *base = reinterpret_cast<const void *>(b);
+    return true;
+}
+
 extern "C" int hb_ipc_export(const void *device_ptr, hb_ipc_mem *out) {
     HB_REQUIRE(device_ptr && out, HB_ERR_INVALID, "hb_ipc_export: null argument");
+    // a CUDA IPC handle names a whole allocation: a pointer into the middle of one (e.g. a tensor carved out of a caching
+    // allocator's block) would be opened at the block's base on the other side and the halo rows would land elsewhere
+    const void *base = nullptr;
+    HB_REQUIRE(!allocation_base(device_ptr, &base) || base == device_ptr, HB_ERR_INVALID,
+               "hb_ipc_export: %p is not the base of its allocation (%p); allocate strip buffers with hb_image_create", device_ptr, base);
     static_assert(sizeof(cudaIpcMemHandle_t) == HB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t h;
     int rc = check_cuda(cudaIpcGetMemHandle(&h, const_cast<void *>(device_ptr)), "cudaIpcGetMemHandle()");

@@ -320,6 +320,18 @@ def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
             np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
 
 
+# ------------------------------------------------------------------ CUDA IPC export guard
+def test_ipc_export_refuses_pointers_inside_an_allocation(hb, dev):
+    """a CUDA IPC handle names a whole allocation: exporting a pointer into the middle of one must fail loudly
+    (the peer would map the allocation's base and the halo rows would land in the wrong place)"""
+    import ctypes as C
+    buf = hb.alloc_image(A.F32, 256, 64, device=dev)          # a whole allocation (hb_image_create)
+    mem = A.hb_ipc_mem()
+    assert hb.lib().hb_ipc_export(C.c_void_p(buf.data_ptr()), C.byref(mem)) == 0
+    assert hb.lib().hb_ipc_export(C.c_void_p(buf.data_ptr() + 4096), C.byref(mem)) == A.HB_ERR_INVALID
+    assert b"not the base of its allocation" in hb.lib().hb_last_error()
+
+
 # ------------------------------------------------------------------ CUDA graphs (the reference's -use-graph mode)
 def test_graph_replay_of_multi_kernel_pipelines(hb, oracle, dev):
     """hb_graph_begin / hb_graph_end capture the nine kernels of the unfused Harris pipeline and a pyramid traversal;
