@@ -320,6 +320,53 @@ def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
             np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
 
 
+# ------------------------------------------------------------------ randomised sweep
+def test_randomised_sweep_gpu_vs_oracle(hb, oracle, dev):
+    """Seeded fuzz over shapes (1 px up to several tiles, widths that break every alignment assumption), boundary modes,
+    padded / dense rows and operator families: the CUDA path must equal the oracle bit for bit."""
+    import torch
+    rng = np.random.default_rng(4242)
+    ops = ("gauss3", "gauss5", "gauss7", "dom3", "dom5", "conv5", "conv7", "max3", "min5", "box3", "sobel5i", "lap5i", "rgba5", "hist")
+    for case in range(56):
+        op = ops[case % len(ops)]
+        b = int(rng.choice([A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT]))
+        size = 5 if op in ("sobel5i", "lap5i", "rgba5", "hist") else int(op[-1])
+        lo = 1 if b in (A.CLAMP, A.CONSTANT) else size // 2 + 1
+        h = int(rng.integers(lo, 150))
+        w = int(rng.choice([rng.integers(lo, 40), rng.integers(100, 700), 128, 256, 257, 511]))
+        w = max(w, lo)
+        padded = bool(rng.integers(0, 2))
+        seed = 3000 + case
+        msg = f"case {case}: {op} {h}x{w} boundary {b} padded {padded}"
+        if op == "hist":
+            img = synth.image_np("float32", w, h, seed=seed, scale=254.99)
+            nb = int(rng.choice([16, 256, 1000]))
+            np.testing.assert_array_equal(hb.binning(to_dev(hb, img, dev, padded), nb), oracle.binning(img, nb), err_msg=msg)
+            continue
+        if op == "rgba5":
+            img = cases.rgba_image(h, w, seed=seed)
+            spec = S.gaussian_blur(M.GAUSS5, b)
+            np.testing.assert_array_equal(to_np(hb.local_op(spec, to_dev(hb, img, dev))), oracle.local_op_x4(spec, img), err_msg=msg)
+            continue
+        if op.startswith("gauss"):
+            img, spec = synth.image_np("uint8", w, h, seed=seed), S.gaussian_blur(M.GAUSS[size], b)
+        elif op in ("dom3", "dom5"):
+            img = synth.image_np("float32", w, h, seed=seed)
+            spec = S.domain_reduce_f32((M.SOBEL3_Y if op == "dom3" else M.SOBEL5_X).astype(np.float32), b)
+        elif op in ("conv5", "conv7"):
+            img, spec = synth.image_np("float32", w, h, seed=seed), S.convolve_f32(M.GAUSS[size], b)
+        elif op in ("max3", "min5"):
+            img, spec = synth.image_np("uint8", w, h, seed=seed), S.minmax_u8(size, size, op == "max3", b)
+        elif op == "box3":
+            img, spec = synth.image_np("uint8", w, h, seed=seed), S.box_blur_u8(3, 3, b)
+        elif op == "sobel5i":
+            img, spec = synth.image_np("uint8", w, h, seed=seed), S.sobel_u8(M.SOBEL5_Y, b)      # separable integer mask
+        else:
+            img, spec = synth.image_np("uint8", w, h, seed=seed), S.laplace_u8(M.LAPLACE5, b)    # not separable
+        got = to_np(hb.local_op(spec, to_dev(hb, img, dev, padded)))
+        np.testing.assert_array_equal(got, oracle.local_op(spec, img), err_msg=msg)
+
+
 # ------------------------------------------------------------------ CUDA IPC export guard
 def test_ipc_export_refuses_pointers_inside_an_allocation(hb, dev):
     """a CUDA IPC handle names a whole allocation: exporting a pointer into the middle of one must fail loudly
