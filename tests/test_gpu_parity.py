@@ -367,6 +367,50 @@ def test_randomised_sweep_gpu_vs_oracle(hb, oracle, dev):
         np.testing.assert_array_equal(got, oracle.local_op(spec, img), err_msg=msg)
 
 
+def test_randomised_sweep_pipelines_gpu_vs_oracle(hb, oracle, dev):
+    """Seeded fuzz over the multi-kernel paths: fused Harris, pyramid traversals (even sizes take the fused level
+    kernels, odd ones the general mapping), interpolating point operators, point arithmetic and reductions."""
+    import torch
+    rng = np.random.default_rng(777)
+    for case in range(10):                                   # fused Harris vs the 9-kernel oracle pipeline
+        h, w = int(rng.integers(1, 140)), int(rng.choice([rng.integers(1, 60), rng.integers(100, 520), 128, 129]))
+        img = synth.blocks_np(w, h, seed=500 + case)
+        np.testing.assert_array_equal(to_np(hb.harris(to_dev(hb, img, dev, bool(case & 1)))), oracle.harris(img), err_msg=f"harris {h}x{w}")
+    for case in range(8):                                    # pyramids
+        depth = int(rng.integers(2, 5))
+        sz = int(rng.choice([3, 5, 7]))
+        unit = 1 << (depth - 1)
+        if case & 1:                                         # every level even -> fused kernels
+            h, w = unit * int(rng.integers(2, 40)), unit * int(rng.integers(2, 60))
+        else:                                                # arbitrary sizes -> mixed / general kernels
+            h, w = int(rng.integers(unit * 2, 200)), int(rng.integers(unit * 2, 300))
+        img = synth.image_np("float32", w, h, seed=600 + case)
+        og, ol = oracle.pyramid(img, depth, M.GAUSS[sz])
+        pg = hb.Pyramid(to_dev(hb, img, dev), depth)
+        pl = hb.Pyramid(torch.zeros_like(pg.levels[0]), depth)
+        hb.pyramid_traverse(pg, pl, M.GAUSS[sz])
+        for lv in range(depth):
+            np.testing.assert_array_equal(to_np(pg.levels[lv]), og[lv], err_msg=f"pyramid {h}x{w} depth {depth} mask {sz} gaus level {lv}")
+            np.testing.assert_array_equal(to_np(pl.levels[lv]), ol[lv], err_msg=f"pyramid {h}x{w} depth {depth} mask {sz} lap level {lv}")
+    for case in range(10):                                   # NN / LF accessors at arbitrary scale factors
+        h, w = int(rng.integers(2, 90)), int(rng.integers(2, 130))
+        oh, ow = int(rng.integers(1, 150)), int(rng.integers(1, 200))
+        img = synth.image_np("float32", w, h, seed=700 + case)
+        ip = [A.INTERP_NN, A.INTERP_LF][case & 1]
+        got = hb.point_op(A.POINT_COPY, [to_dev(hb, img, dev)], A.F32, (oh, ow), [ip])
+        np.testing.assert_array_equal(to_np(got), oracle.point_op(A.POINT_COPY, [img], A.F32, (oh, ow), [ip]), err_msg=f"interp {ip} {h}x{w}->{oh}x{ow}")
+    for case in range(8):                                    # point arithmetic (streaming path incl. row tails) + reductions
+        h, w = int(rng.integers(1, 70)), int(rng.choice([rng.integers(1, 50), rng.integers(300, 1100), 1024, 1027]))
+        a, b2 = synth.image_np("float32", w, h, seed=800 + case), synth.image_np("float32", w, h, seed=900 + case)
+        da, db = to_dev(hb, a, dev, bool(case & 1)), to_dev(hb, b2, dev, bool(case & 1))
+        for op in (A.POINT_SUB, A.POINT_ADD, A.POINT_BLEND, A.POINT_MUL):
+            np.testing.assert_array_equal(to_np(hb.point_op(op, [da, db], A.F32)), oracle.point_op(op, [a, b2], A.F32), err_msg=f"point {op} {h}x{w}")
+        mn, mx, sm = hb.reduce_minmaxsum(da)
+        assert np.float32(mn) == a.min() and np.float32(mx) == a.max() and abs(sm - a.astype(np.float64).sum()) <= 1e-5 * abs(a.astype(np.float64).sum()) + 1e-6
+        u8 = synth.image_np("uint8", w, h, seed=950 + case)
+        assert hb.reduce(to_dev(hb, u8, dev, bool(case & 1)), A.MAX) == u8.max() and hb.reduce(to_dev(hb, u8, dev), A.MIN) == u8.min()
+
+
 # ------------------------------------------------------------------ CUDA IPC export guard
 def test_ipc_export_refuses_pointers_inside_an_allocation(hb, dev):
     """a CUDA IPC handle names a whole allocation: exporting a pointer into the middle of one must fail loudly
