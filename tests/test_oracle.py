@@ -242,6 +242,32 @@ def test_randomised_sweep_vs_reference(ref):
         np.testing.assert_array_equal(got, want, err_msg=f"case {case}: {op} {h}x{w} boundary {b}")
 
 
+def test_randomised_sweep_rgba_and_histogram_vs_reference(ref):
+    """uchar4 operators (per-channel oracle) and the histogram against the RGBA / Histogram samples run by the reference
+    DSL, over random shapes and boundary modes"""
+    rng = np.random.default_rng(99)
+    for case in range(16):
+        b = int(rng.choice([A.CLAMP, A.MIRROR, A.REPEAT, A.CONSTANT]))
+        lo = 1 if b in (A.CLAMP, A.CONSTANT) else 4
+        h, w = int(rng.integers(lo, 30)), int(rng.integers(lo, 45))
+        img = cases.rgba_image(h, w, seed=2000 + case)
+        kind = case % 4
+        if kind == 0:
+            sz = int(rng.choice([3, 5, 7])) if lo == 4 or min(h, w) >= 1 else 3
+            want, got = ref.ref_gaussian_rgba(img, M.GAUSS[sz], b), ref.local_op_x4(S.gaussian_blur(M.GAUSS[sz], b), img)
+        elif kind == 1:
+            want, got = ref.ref_laplace_rgba(img, M.LAPLACE5, b), ref.local_op_x4(S.laplace_u8(M.LAPLACE5, b, add=0), img)
+        elif kind == 2:
+            want, got = ref.ref_dilate_rgba(img, 5, 5, b), ref.local_op_x4(S.minmax_u8(5, 5, True, b), img)
+        else:
+            want, got = ref.ref_box_rgba(img, 3, 3, b), ref.local_op_x4(S.box_blur_u8(3, 3, b), img)
+        np.testing.assert_array_equal(got, want, err_msg=f"case {case}: kind {kind} {h}x{w} boundary {b}")
+    for case in range(6):
+        h, w, nb = int(rng.integers(1, 60)), int(rng.integers(1, 90)), int(rng.choice([2, 17, 256, 999]))
+        img = synth.image_np("float32", w, h, seed=2100 + case, scale=254.99)
+        np.testing.assert_array_equal(ref.binning(img, nb), ref.ref_sample_histogram_f32(img, nb), err_msg=f"hist {h}x{w} bins {nb}")
+
+
 def test_repeat_divergence_with_offset_accessor(ref):
     """DSL repeat adds lower+upper once (dsl/image.hpp:296-300); emitted code loops +-size
     (lib/AST/BorderHandling.cpp:59-74).  Equal when lower == 0, different for an offset window:
