@@ -327,6 +327,29 @@ BIN *hipaccApplyBinning(const HipaccAccessor<T> &acc, unsigned num_bins, int ind
     sc.done("binning", print_timing);
     return bins;
 }
+// -use-graph (runtime/hipacc_cu_standalone.hpp:331-356): record every launch issued on the execution parameter's stream
+// between hipaccGraphBegin and hipaccGraphEnd, replay them with hipaccGraphLaunch.  The stream must not be the default one.
+class HipaccGraph {
+    hb_graph *g_ = nullptr;
+
+  public:
+    HipaccGraph() = default;
+    HipaccGraph(const HipaccGraph &) = delete;
+    HipaccGraph &operator=(const HipaccGraph &) = delete;
+    ~HipaccGraph() { hb_graph_destroy(g_); }
+    hb_graph **slot() { hb_graph_destroy(g_); g_ = nullptr; return &g_; }
+    hb_graph *get() const { return g_; }
+};
+inline void hipaccGraphBegin(HipaccExecutionParameterCuda const &ep) {
+    hipacc_b200::check(hb_graph_begin(ep ? ep->get_stream() : nullptr), "hipaccGraphBegin()");
+}
+inline void hipaccGraphEnd(HipaccExecutionParameterCuda const &ep, HipaccGraph &graph) {
+    hipacc_b200::check(hb_graph_end(ep ? ep->get_stream() : nullptr, graph.slot()), "hipaccGraphEnd()");
+}
+inline void hipaccGraphLaunch(const HipaccGraph &graph, HipaccExecutionParameterCuda const &ep) {
+    hipacc_b200::check(hb_graph_launch(graph.get(), ep ? ep->get_stream() : nullptr), "hipaccGraphLaunch()");
+}
+
 // fused min + max + sum in one pass over HBM (float images)
 inline void hipaccApplyReductionMinMaxSum(const HipaccAccessor<float> &acc, float &mn, float &mx, float &sum,
                                           HipaccExecutionParameterCuda const &ep = nullptr) {

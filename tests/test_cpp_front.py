@@ -39,6 +39,11 @@ def test_program_compiles_and_links(name):
     assert os.path.exists(exe)
 
 
+def test_runtime_graph_wrappers_compile():
+    exe = compile_program("compile_only_graph")
+    assert os.path.exists(exe)
+
+
 def test_front_headers_need_no_cuda_toolkit():
     """The including translation unit sees only the C ABI: no cuda_runtime.h, no torch."""
     for h in ("hipacc.hpp", "hipacc_rt.hpp"):
