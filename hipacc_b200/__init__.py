@@ -59,6 +59,8 @@ def lib():
         L.hb_image_copy.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_image_copy_region.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_stream_synchronize.argtypes = [C.c_void_p]
+        L.hb_stream_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.hb_stream_destroy.argtypes = [C.c_void_p]
         L.hb_graph_begin.argtypes = [C.c_void_p]
         L.hb_graph_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.hb_graph_launch.argtypes = [C.c_void_p, C.c_void_p]

@@ -137,7 +137,7 @@ EXPORTS = [
     "hb_init", "hb_device_count", "hb_sm_count", "hb_set_log_callback", "hb_last_error",
     "hb_image_create", "hb_image_destroy", "hb_image_wrap", "hb_image_write", "hb_image_read",
     "hb_image_copy", "hb_image_copy_region", "hb_image_write_region_async", "hb_image_read_region_async", "hb_set_timing", "hb_last_kernel_ms", "hb_launch_count",
-    "hb_stream_synchronize", "hb_graph_begin", "hb_graph_end", "hb_graph_launch", "hb_graph_destroy",
+    "hb_stream_synchronize", "hb_stream_create", "hb_stream_destroy", "hb_graph_begin", "hb_graph_end", "hb_graph_launch", "hb_graph_destroy",
     "hb_local_op", "hb_bilateral", "hb_point_op",
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",

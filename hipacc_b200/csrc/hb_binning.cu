@@ -14,6 +14,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <mutex>
 
 namespace hb {
 
@@ -156,6 +157,7 @@ struct BinScratch {
     int cap = 0;
 };
 static BinScratch g_bin[16];
+static std::mutex g_bin_mutex;   // the blocking form owns the per-device scratch for the whole call
 
 static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStream_t s, const char *who) {
     hb_view v = norm_view(d->in);
@@ -208,6 +210,8 @@ extern "C" int hb_binning_async(const hb_binning_desc *d, uint32_t *bins_device,
 extern "C" int hb_binning(const hb_binning_desc *d, uint32_t *bins_host, void *stream) {
     HB_REQUIRE(d && bins_host, HB_ERR_INVALID, "hb_binning: null argument");
     HB_REQUIRE(d->num_bins > 0 && d->num_bins <= (1 << 22), HB_ERR_INVALID, "hb_binning: num_bins %d out of range", d->num_bins);
+    HB_REQUIRE(!stream_is_capturing((cudaStream_t)stream), HB_ERR_INVALID, "hb_binning blocks and cannot be captured; use hb_binning_async");
+    std::lock_guard<std::mutex> lock(g_bin_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     BinScratch &sc = g_bin[dev & 15];

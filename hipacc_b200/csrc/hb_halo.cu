@@ -40,14 +40,12 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void spin_until(int *flag, int want, int *err) {
+__device__ __forceinline__ bool spin_until(int *flag, int want) {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < want) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
-            *err = 1;
-            break;
-        }
+        if (clock64() - t0 > 4000000000LL) return false;  // ~2 s at 1.9 GHz
     }
+    return true;
 }
 
 __device__ __forceinline__ void push_rows(unsigned char *dst, size_t dpitch, const unsigned char *src, size_t spitch, size_t row_bytes, int rows) {
@@ -72,27 +70,47 @@ struct HaloBatch {
 
 // one CTA per strip buffer of the batch (e.g. the Gaussian and the Laplacian level of a pyramid transition): the
 // exchanges of a batch run concurrently in one launch
+// A wait that times out (a neighbour never arrived) must not let the exchange carry on: pushing into ghost rows the
+// neighbour may still be reading, or running the next operator on ghost rows that never arrived, would corrupt results
+// silently.  The kernel then raises ctrl[5], skips the push / publish steps and POISONS the exchange counter (negative),
+// so every later exchange on this control block returns immediately and hb_halo_status reports the failure.
+constexpr int kPoisoned = -(1 << 30);
+
 __global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_constant__ HaloBatch batch) {
     const HaloParams &p = batch.p[blockIdx.x];
+    __shared__ int ok;
     const int e = p.ctrl[0];   // read by every thread before thread 0 advances it (barriers below)
+    if (e < 0) return;         // poisoned by an earlier timeout
     if (threadIdx.x == 0) {
         // my ghost rows of exchange e-1 are consumed: the neighbours may overwrite them
         if (p.up_ctrl) st_release_sys(p.up_ctrl + 4, e);      // I am the upper neighbour's lower neighbour
         if (p.down_ctrl) st_release_sys(p.down_ctrl + 3, e);
-        if (p.up_ctrl) spin_until(p.ctrl + 3, e, p.ctrl + 5);
-        if (p.down_ctrl) spin_until(p.ctrl + 4, e, p.ctrl + 5);
+        bool good = true;
+        if (p.up_ctrl) good = spin_until(p.ctrl + 3, e) && good;
+        if (p.down_ctrl) good = spin_until(p.ctrl + 4, e) && good;
+        ok = good ? 1 : 0;
     }
     __syncthreads();
-    if (p.up_dst) push_rows(p.up_dst, p.up_pitch, p.buf + (size_t)p.gt * p.pitch, p.pitch, p.row_bytes, p.R);
-    if (p.down_dst) push_rows(p.down_dst, p.down_pitch, p.buf + (size_t)(p.gt + p.rows - p.R) * p.pitch, p.pitch, p.row_bytes, p.R);
-    __threadfence_system();
+    if (ok) {
+        if (p.up_dst) push_rows(p.up_dst, p.up_pitch, p.buf + (size_t)p.gt * p.pitch, p.pitch, p.row_bytes, p.R);
+        if (p.down_dst) push_rows(p.down_dst, p.down_pitch, p.buf + (size_t)(p.gt + p.rows - p.R) * p.pitch, p.pitch, p.row_bytes, p.R);
+        __threadfence_system();
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (p.up_ctrl) st_release_sys(p.up_ctrl + 2, e + 1);   // data from its lower neighbour
-        if (p.down_ctrl) st_release_sys(p.down_ctrl + 1, e + 1);
-        if (p.up_ctrl) spin_until(p.ctrl + 1, e + 1, p.ctrl + 5);
-        if (p.down_ctrl) spin_until(p.ctrl + 2, e + 1, p.ctrl + 5);
-        p.ctrl[0] = e + 1;
+        bool good = ok != 0;
+        if (good) {
+            if (p.up_ctrl) st_release_sys(p.up_ctrl + 2, e + 1);   // data from its lower neighbour
+            if (p.down_ctrl) st_release_sys(p.down_ctrl + 1, e + 1);
+            if (p.up_ctrl) good = spin_until(p.ctrl + 1, e + 1) && good;
+            if (p.down_ctrl) good = spin_until(p.ctrl + 2, e + 1) && good;
+        }
+        if (good) {
+            p.ctrl[0] = e + 1;
+        } else {
+            p.ctrl[5] = 1;
+            p.ctrl[0] = kPoisoned;
+        }
         __threadfence();
     }
 }
@@ -168,7 +186,7 @@ extern "C" int hb_halo_status(const void *ctrl, int *exchanges, int *timed_out) 
     HB_REQUIRE(ctrl, HB_ERR_INVALID, "hb_halo_status: null argument");
     int h[CTRL_INTS];
     int rc = check_cuda(cudaMemcpy(h, ctrl, sizeof(h), cudaMemcpyDeviceToHost), "cudaMemcpy(halo control block)");
-    if (exchanges) *exchanges = h[0];
+    if (exchanges) *exchanges = h[0] < 0 ? -1 : h[0];   // -1: poisoned after a timeout
     if (timed_out) *timed_out = h[5];
     return rc;
 }

@@ -350,6 +350,10 @@ extern "C" int hb_harris(const hb_harris_desc *d, void *stream) {
     hb_view in = norm_view(d->in), out = norm_view(d->out);
     HB_REQUIRE(view_ok(in) && view_ok(out) && in.dtype == HB_U8 && out.dtype == HB_U8, HB_ERR_INVALID, "hb_harris: needs valid u8 views");
     HB_REQUIRE(in.width == out.width && in.height == out.height, HB_ERR_INVALID, "hb_harris: input and output regions must have the same size");
+    // the fused Sobel + Gaussian reads two rows beyond an interior strip edge: with fewer ghost rows the row index would
+    // be clamped inside the window and the result would silently differ from the unsharded pipeline
+    HB_REQUIRE((in.ghost_top == 0 || in.ghost_top >= 2) && (in.ghost_bottom == 0 || in.ghost_bottom >= 2), HB_ERR_INVALID,
+               "hb_harris: a sharded strip needs >= 2 ghost rows per interior side (got %d / %d)", in.ghost_top, in.ghost_bottom);
     HarrisParams p;
     memset(&p, 0, sizeof(p));
     p.in = static_cast<const uchar *>(in.data); p.out = static_cast<uchar *>(out.data);

@@ -27,9 +27,14 @@ inline int check_cuda(cudaError_t e, const char *what) {
 struct OpScope {
     cudaStream_t stream;
     const char *name;
+    bool timed;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     OpScope(cudaStream_t s, const char *n);
     int finish();  // returns status of the launches issued inside the scope
 };
+bool stream_is_capturing(cudaStream_t s);
+// per-(device, stream) reduction scratch must exist before a capture starts (hb_reduce.cu)
+int reserve_reduce_scratch(cudaStream_t s);
 
 inline hb_view norm_view(const hb_view &v) {
     hb_view o = v;

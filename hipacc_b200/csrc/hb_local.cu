@@ -79,12 +79,16 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
                     for (int i = 0; i < 4; ++i) {
                         constexpr int base = HXP - HX;
                         const int odd = (base + i) & 1;   // compile-time after unrolling: first tap in an odd register
-                        if (odd) af[r][i] = __fadd_rn(af[r][i], __fmul_rn(p.coef.f[dy * SX], wf[base + i]));
+                        // the first visited tap initialises the accumulator (dsl/kernel.hpp:250), it is not added to zero
+                        if (odd) {
+                            const float p0 = __fmul_rn(p.coef.f[dy * SX], wf[base + i]);
+                            af[r][i] = dy == 0 ? p0 : __fadd_rn(af[r][i], p0);
+                        }
 #pragma unroll
                         for (int dx = odd; dx + 1 < SX; dx += 2) {
                             float p0, p1;
                             mul2_rn(wf[base + i + dx], wf[base + i + dx + 1], &p.cpair[odd][dy][dx - odd], p0, p1);
-                            af[r][i] = __fadd_rn(__fadd_rn(af[r][i], p0), p1);
+                            af[r][i] = __fadd_rn(dy == 0 && dx == 0 ? p0 : __fadd_rn(af[r][i], p0), p1);
                         }
                         if (((SX - odd) & 1) != 0) af[r][i] = __fadd_rn(af[r][i], __fmul_rn(p.coef.f[dy * SX + SX - 1], wf[base + i + SX - 1]));
                     }
@@ -95,8 +99,8 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
                         for (int i = 0; i < 4; i += 2) {   // two adjacent channel elements share the coefficient
                             float p0, p1;
                             mul2_rn(wf[HXP - HX + i + dx * CH], wf[HXP - HX + i + 1 + dx * CH], p.cdup[dy * SX + dx], p0, p1);
-                            af[r][i] = __fadd_rn(af[r][i], p0);
-                            af[r][i + 1] = __fadd_rn(af[r][i + 1], p1);
+                            af[r][i] = dy == 0 && dx == 0 ? p0 : __fadd_rn(af[r][i], p0);
+                            af[r][i + 1] = dy == 0 && dx == 0 ? p1 : __fadd_rn(af[r][i + 1], p1);
                         }
                 }
             }
@@ -135,7 +139,8 @@ __global__ void __launch_bounds__(BX *BY) local_tiled_kernel(const __grid_consta
                     TS v;
                     if (VAR == 0 || p.tap == HB_TAP_MUL) v = mul_rn(coef_of<TS>(p, k), pix);
                     else v = pix;
-                    acc[r][i] = fold<TS>(acc[r][i], v, mode);
+                    // first visited tap initialises (dsl/kernel.hpp:250,279): tap 0 when every tap is visited
+                    acc[r][i] = (VAR == 0 ? k == 0 : k == p.first_tap) ? v : fold<TS>(acc[r][i], v, mode);
                 }
             }
         }
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(256) local_generic_kernel(const __grid_constan
             if (!((p.dom[k >> 5] >> (k & 31)) & 1u)) continue;
             const TS pix = tile[(ty + dy) * pw + tx + dx];
             const TS v = p.tap == HB_TAP_MUL ? mul_rn(coef_of<TS>(p, k), pix) : pix;
-            acc = fold<TS>(acc, v, mode);
+            acc = k == p.first_tap ? v : fold<TS>(acc, v, mode);
         }
     static_cast<TO *>(p.out)[(size_t)(p.out_oy + gy) * p.out_stride + p.out_ox + gx] = epilogue<TO>(acc, p);
 }
@@ -318,13 +323,14 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
                "hb_local_op: float mask with an integer accumulator is not supported");
     const int n = d->size_x * d->size_y;
     int visited = 0;
+    p.first_tap = -1;
     for (int k = 0; k < n; ++k) {
         bool on = true;
         if (d->kind == HB_LOCAL_REDUCE_DOMAIN) {
             if (d->domain) on = d->domain[k] != 0;
             else if (d->tap == HB_TAP_MUL) on = d->coef_f32 ? d->coef_f32[k] != 0.0f : d->coef_s32[k] != 0;
         }
-        if (on) { p.dom[k >> 5] |= 1u << (k & 31); ++visited; }
+        if (on) { p.dom[k >> 5] |= 1u << (k & 31); ++visited; if (p.first_tap < 0) p.first_tap = k; }
         if (d->tap == HB_TAP_MUL) {
             // holes contribute coef 0 in the SUM fast path (exact: x + 0 == x)
             if (facc) p.coef.f[k] = on ? (d->coef_f32 ? d->coef_f32[k] : (float)d->coef_s32[k]) : 0.0f;
@@ -340,7 +346,10 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
             }
         for (int k = 0; k < n; ++k) p.cdup[k][0] = p.cdup[k][1] = p.coef.f[k];
     }
-    const bool fast = d->reduce_mode == HB_REDUCE_SUM && d->tap == HB_TAP_MUL;
+    // SUM-of-products fast variant: Domain holes ride along as zero coefficients.  That is exact for integer pixels
+    // (0 * pixel adds nothing); for FLOAT pixels a hole over an inf / NaN pixel would poison the sum although the DSL
+    // never visits that tap, so float images with holes take the domain-testing variant.
+    const bool fast = d->reduce_mode == HB_REDUCE_SUM && d->tap == HB_TAP_MUL && (visited == n || in.dtype != HB_F32);
 
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_local_op");

@@ -22,6 +22,7 @@ struct LocalParams {
     float cval_f;
     int cval_i;
     unsigned dom[6];  // bit k: tap k (row-major) is visited
+    int first_tap;    // first visited tap: it initialises the accumulator (dsl/kernel.hpp:250,279)
     union {
         float f[kMaxTaps];
         int i[kMaxTaps];

@@ -6,6 +6,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 namespace hb {
@@ -17,7 +18,12 @@ static thread_local std::string g_last_error;
 static thread_local float g_last_ms = 0.0f;  // thread_local like HipaccKernelTimingBase (hipacc_base_standalone.hpp:35-39)
 static int g_device = -1;
 static int g_sms = 0;
-static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+// timing events: one pair per host thread and device (the reference's timing singleton is thread_local too), so
+// two threads that time operators on different streams do not share an event
+struct TimingEvents {
+    cudaEvent_t ev0[16] = {}, ev1[16] = {};
+};
+static thread_local TimingEvents t_events;
 
 void set_last_error(const std::string &s) { g_last_error = s; }
 
@@ -41,19 +47,32 @@ int sm_count() {
     return g_sms;
 }
 
-OpScope::OpScope(cudaStream_t s, const char *n) : stream(s), name(n) {
-    if (g_timing) {
-        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-        cudaEventRecord(g_ev0, stream);
+bool stream_is_capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// Timing brackets the operator with events and SYNCHRONISES (the reference's print_timing).  Inside a stream capture
+// (hb_graph_begin .. hb_graph_end) an event synchronise is illegal and would invalidate the capture, so a captured
+// operator is never timed: the launch is recorded into the graph and hb_last_kernel_ms keeps its previous value.
+OpScope::OpScope(cudaStream_t s, const char *n) : stream(s), name(n), timed(false) {
+    if (g_timing && !stream_is_capturing(s)) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 15;
+        if (!t_events.ev0[dev]) { cudaEventCreate(&t_events.ev0[dev]); cudaEventCreate(&t_events.ev1[dev]); }
+        ev0 = t_events.ev0[dev]; ev1 = t_events.ev1[dev];
+        timed = cudaEventRecord(ev0, stream) == cudaSuccess;
     }
 }
 int OpScope::finish() {
     int rc = check_cuda(cudaGetLastError(), name);
-    if (g_timing) {
-        cudaEventRecord(g_ev1, stream);
-        rc |= check_cuda(cudaEventSynchronize(g_ev1), name);
+    if (timed) {
+        cudaEventRecord(ev1, stream);
+        rc |= check_cuda(cudaEventSynchronize(ev1), name);
         float ms = 0.0f;
-        cudaEventElapsedTime(&ms, g_ev0, g_ev1);
+        cudaEventElapsedTime(&ms, ev0, ev1);
         g_last_ms = ms;
     }
     return rc ? HB_ERR_CUDA : HB_OK;
@@ -125,12 +144,28 @@ bool make_tile_map(CUtensorMap *out, const void *base, int dtype, int img_w, int
     }
     const CUtensorMapL2promotion l2 = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    // descriptors are cached per (pointer, extent, pitch, box): an operator that runs every frame on the same image
+    // does not pay the driver's encode on each launch
+    struct Key {
+        const void *base; int dtype, w, h, stride, bw, bh, promo;
+        bool operator<(const Key &o) const { return memcmp(this, &o, sizeof(Key)) < 0; }
+    };
+    static std::mutex mu;
+    static std::map<Key, CUtensorMap> cache;
+    Key key;
+    memset(&key, 0, sizeof(key));
+    key.base = base; key.dtype = dtype; key.w = img_w; key.h = img_h; key.stride = stride_px; key.bw = box_w; key.bh = box_h; key.promo = promo;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
     const CUresult r = fn(out, dt, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_NONE, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         log_msg(1, "WARNING: cuTensorMapEncodeTiled failed (%d) for a %dx%d image, box %dx%d", (int)r, img_w, img_h, box_w, box_h);
         return false;
     }
+    if (cache.size() >= 256) cache.clear();
+    cache.emplace(key, *out);
     return true;
 }
 
@@ -169,6 +204,18 @@ void hb_set_timing(int enabled) { g_timing = enabled != 0; }
 float hb_last_kernel_ms(void) { return g_last_ms; }
 long long hb_launch_count(void) { return g_launches.load(); }
 int hb_stream_synchronize(void *stream) { return check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize()"); }
+
+int hb_stream_create(void **stream) {
+    HB_REQUIRE(stream, HB_ERR_INVALID, "hb_stream_create: null argument");
+    cudaStream_t s = nullptr;
+    int rc = check_cuda(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreateWithFlags()");
+    *stream = s;
+    return rc;
+}
+int hb_stream_destroy(void *stream) {
+    if (!stream) return HB_OK;
+    return check_cuda(cudaStreamDestroy((cudaStream_t)stream), "cudaStreamDestroy()");
+}
 
 int hb_image_create(int dtype, int width, int height, int alignment, hb_view *out) {
     HB_REQUIRE(out && width > 0 && height > 0 && dtype >= HB_U8 && dtype <= HB_U8X4, HB_ERR_INVALID, "hb_image_create: bad arguments");
@@ -244,6 +291,10 @@ int hb_image_read_region_async(const hb_view *region, void *host, size_t host_pi
 
 int hb_graph_begin(void *stream) {
     HB_REQUIRE(stream, HB_ERR_INVALID, "hb_graph_begin: capture needs a non-default stream");
+    // allocations are illegal while capturing: the scratch a captured reduction bakes into the graph is reserved now
+    // (one set per stream, never reallocated, so replays stay valid)
+    int rc = reserve_reduce_scratch((cudaStream_t)stream);
+    if (rc) return rc;
     return check_cuda(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture()");
 }
 int hb_graph_end(void *stream, hb_graph **out) {

@@ -180,6 +180,24 @@ class P2PHalo:
             return
         self.hb._check(self.L.hb_halo_exchange(C.byref(self.desc), self.hb.stream_ptr(stream)), "hb_halo_exchange")
 
+    def close(self):
+        """Unmap the neighbours' memory and free the control block (after the last exchange has completed on every
+        rank: the neighbours write into this control block)."""
+        if self.desc is None:
+            return
+        for pb, pk in self._peers.values():
+            self.L.hb_ipc_close(pb)
+            self.L.hb_ipc_close(pk)
+        self._peers = {}
+        self.L.hb_halo_ctrl_destroy(self.ctrl)
+        self.desc = None
+
+    def check(self):
+        """raise if an exchange on this control block ever timed out (the block is poisoned afterwards)"""
+        n, timed_out = self.status()
+        if timed_out or n < 0:
+            raise RuntimeError(f"rank {self.plan.rank}: a halo exchange timed out waiting for a neighbour; ghost rows are stale")
+
     @staticmethod
     def exchange_batch(halos, stream=None):
         """several strip buffers in ONE launch (hb_halo_exchange_batch, one CTA per buffer)"""

@@ -125,6 +125,10 @@ float hb_last_kernel_ms(void);
 /* launches issued by this library since process start (bench.py's gpu_launches) */
 long long hb_launch_count(void);
 int hb_stream_synchronize(void *stream);
+/* The stream a HipaccExecutionParameterCuda carries (runtime/hipacc_cu.hpp:234-245) is the user's cudaStream_t; host
+ * code that does not include the CUDA headers creates one here (non-blocking with respect to the default stream). */
+int hb_stream_create(void **stream);
+int hb_stream_destroy(void *stream);
 
 /* ------------------------------------------------------------------ CUDA graphs */
 /*

@@ -281,6 +281,129 @@ def test_reduce_vs_golden(hb, dev):
     assert abs(sm - float(g["reduce_sum"][0])) <= 1e-5 * abs(sm)
 
 
+@pytest.mark.parametrize("dt", ["uint8", "int8", "int16", "int32"])
+@pytest.mark.parametrize("shape,roi", [((39, 66), None), ((3, 1025), None), ((517, 391), (300, 200, 33, 17)), ((1024, 2048), None)])
+def test_reduce_integer_types_all_modes(hb, dev, dt, shape, roi):
+    """Integer images fold in the pixel type's modular arithmetic (data_t reduce(data_t, data_t), dsl/kernel.hpp:121-151):
+    SUM and PROD wrap, so the vectorised kernel is bit-exact whatever its order."""
+    raw = synth.image_np("uint8", shape[1], shape[0], seed=47)
+    img = raw.astype(dt) if dt in ("uint8", "int8") else (raw.astype(np.int32) * 37 - 4000).astype(dt)
+    d = to_dev(hb, img, dev)
+    sub = img if roi is None else img[roi[3]:roi[3] + roi[1], roi[2]:roi[2] + roi[0]]
+    bits = 8 * img.dtype.itemsize
+    want_sum = np.array([int(sub.astype(np.int64).sum()) & ((1 << bits) - 1)], dtype=np.uint64).astype(f"uint{bits}").view(dt)[0]
+    assert hb.reduce(d, A.SUM, roi) == want_sum
+    assert hb.reduce(d, A.MIN, roi) == sub.min() and hb.reduce(d, A.MAX, roi) == sub.max()
+    # PROD modulo 2^bits: odd values keep the product non-zero
+    odd = (img | 1).astype(dt)
+    prod = 1
+    sub_odd = odd if roi is None else odd[roi[3]:roi[3] + roi[1], roi[2]:roi[2] + roi[0]]
+    for v in sub_odd.ravel().tolist()[:20000]:
+        prod = (prod * v) & ((1 << bits) - 1)
+    small = np.ascontiguousarray(sub_odd.ravel()[:20000].reshape(1, -1))
+    assert hb.reduce(to_dev(hb, small, dev), A.PROD) == np.array([prod], dtype=np.uint64).astype(f"uint{bits}").view(dt)[0]
+
+
+def test_reduce_sum_sample_int_4096(hb, dev):
+    """the Reduction_Sum sample's configuration: int 4096 x 4096 (samples-public/2_Global_Operators/Reduction_Sum)"""
+    img = (synth.image_np("uint8", 4096, 4096, seed=48).astype(np.int32) - 90)
+    want = np.array([int(img.astype(np.int64).sum()) & 0xFFFFFFFF], dtype=np.uint64).astype(np.uint32).view(np.int32)[0]
+    assert hb.reduce(to_dev(hb, img, dev), A.SUM) == want
+
+
+def test_reduce_float_prod(hb, dev):
+    f = (0.75 + 0.5 * synth.image_np("float32", 300, 211, seed=49)).astype(np.float32)   # values in [0.75, 1.25): the product stays finite
+    got = hb.reduce(to_dev(hb, f, dev), A.PROD)
+    want = np.exp(np.log(f.astype(np.float64)).sum())
+    assert abs(got - want) <= 1e-5 * abs(want)
+
+
+def test_reduce_nan(hb, dev):
+    """MIN / MAX ignore NaN pixels (fminf / fmaxf).  The reference has no thread-count independent result here: its DSL
+    fold restarts after a NaN (min(a,b) = a < b ? a : b, dsl/math_functions.hpp:349-351), its OpenMP runtime does so per
+    thread chunk -- the documented contract of this library is 'NaNs are skipped'."""
+    f = synth.image_np("float32", 257, 131, seed=50)
+    g = f.copy()
+    g[0, 0] = np.nan
+    g[77, 100] = np.nan
+    g[130, 256] = np.nan
+    mn, mx, sm = hb.reduce_minmaxsum(to_dev(hb, g, dev))
+    assert np.float32(mn) == np.nanmin(g) and np.float32(mx) == np.nanmax(g) and np.isnan(sm)
+    allnan = np.full((5, 9), np.nan, np.float32)
+    mn, mx, _ = hb.reduce_minmaxsum(to_dev(hb, allnan, dev))
+    assert mn == np.inf and mx == -np.inf
+
+
+def test_reductions_on_two_streams_do_not_share_scratch(hb, dev):
+    """per-(device, stream) scratch: reductions in flight on two streams each fold their own partials"""
+    import torch
+    a = synth.image_np("float32", 4096, 2048, seed=51)
+    b = synth.image_np("float32", 4096, 2048, seed=52) * 3.0
+    da, db = to_dev(hb, a, dev), to_dev(hb, b, dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    pa = torch.zeros((64, 4), dtype=torch.float32, device=dev)
+    pb = torch.zeros((64, 4), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    for i in range(64):   # interleaved launches: with one shared ticket the last-CTA folds would mix
+        hb.reduce_minmaxsum_async(da, pa[i], stream=s1)
+        hb.reduce_minmaxsum_async(db, pb[i], stream=s2)
+    torch.cuda.synchronize()
+    for part, img in ((pa, a), (pb, b)):
+        h = part.cpu().numpy()
+        assert (h[:, 0] == img.min()).all() and (h[:, 1] == img.max()).all()
+        sums = np.ascontiguousarray(h[:, 2:4]).view(np.float64).ravel()
+        assert (sums == sums[0]).all() and abs(sums[0] - img.astype(np.float64).sum()) <= 1e-5 * img.astype(np.float64).sum()
+
+
+def test_graph_capture_with_timing_enabled_and_captured_reduction(hb, oracle, dev):
+    """hb_set_timing(1) must not break a capture (captured operators are not timed), and a captured reduction keeps
+    its scratch: a larger reduction between capture and replay does not invalidate the graph."""
+    import torch
+    stream = torch.cuda.Stream(device=dev)
+    f0, f1 = synth.image_np("float32", 640, 333, seed=53), synth.image_np("float32", 640, 333, seed=54)
+    src = to_dev(hb, f0, dev)
+    dst = torch.zeros_like(src)
+    part = torch.zeros(4, dtype=torch.float32, device=dev)
+    spec = S.domain_reduce_f32(M.LAPLACE3.astype(np.float32), A.MIRROR)
+    hb.set_timing(True)
+    try:
+        with torch.cuda.stream(stream):
+            with hb.Graph(stream) as g:   # first use of the reduction on this stream happens INSIDE the capture
+                hb.local_op(spec, src, dst=dst, stream=stream)
+                hb.reduce_minmaxsum_async(dst, part, stream=stream)
+            big = to_dev(hb, synth.image_np("float32", 8192, 2048, seed=55), dev)
+            hb.reduce_minmaxsum(big, stream=stream)   # a larger grid in between
+            for img in (f1, f0):
+                src.copy_(torch.from_numpy(img).to(dev))
+                stream.synchronize()
+                g.launch()
+                stream.synchronize()
+                want = oracle.local_op(spec, img)
+                np.testing.assert_array_equal(to_np(dst), want)
+                h = part.cpu().numpy()
+                assert h[0] == want.min() and h[1] == want.max()
+            g.destroy()
+            hb.local_op(spec, src, dst=dst, stream=stream)   # outside a capture the operator is timed again
+            assert hb.last_kernel_ms() > 0.0
+    finally:
+        hb.set_timing(False)
+
+
+def test_first_tap_initialises_and_holes_skip_non_finite_pixels(hb, oracle, dev):
+    """dsl/kernel.hpp:250,279: the first visited tap initialises the accumulator and Domain holes are never read --
+    an inf / NaN pixel under a hole must not reach the result (dense and 256-byte pitched rows: TMA and tiled paths)."""
+    f = synth.image_np("float32", 300, 200, seed=56)
+    f[50, 60] = np.inf
+    f[120, 7] = np.nan
+    f[0, 0] = -np.inf
+    for m in (M.SOBEL3_X, M.LAPLACE3, np.array([[0, 1, 0], [1, 0, 1], [0, 1, 0]])):
+        spec = S.domain_reduce_f32(m.astype(np.float32), A.CLAMP)
+        want = oracle.local_op(spec, f)
+        for padded in (True, False):
+            got = to_np(hb.local_op(spec, to_dev(hb, f, dev, padded)))
+            np.testing.assert_array_equal(got, want)
+
+
 # ------------------------------------------------------------------ Harris
 @pytest.mark.parametrize("shape", [cases.HARRIS_SHAPE, (200, 333), (33, 129), (5, 7)])
 def test_harris_fused_and_unfused(hb, oracle, dev, shape):
