@@ -166,11 +166,17 @@ int local_sum_full(const hb_local_desc &d, const float *coef) {
         for (int gx = 0; gx < x_lo; ++gx) border(gx);
         const TI *__restrict__ c0 = s.p + (size_t)iy * s.stride + in.offset_x;
         const ptrdiff_t st = s.stride;
+        float cc[SX * SY];   // a copy no lambda captures: it cannot alias the (possibly char-typed) output stores
+        for (int k = 0; k < SX * SY; ++k) cc[k] = coef[k];
+        const float add_v = addend;
+        const bool add_f = add;
 #pragma omp simd
         for (int gx = x_lo; gx < x_hi; ++gx) {
-            float acc = c[0] * (float)c0[gx - hx - hy * st];
-            for (int k = 1; k < SX * SY; ++k) acc = acc + c[k] * (float)c0[gx + (k % SX - hx) + (k / SX - hy) * st];
-            orow[gx] = finish(acc);
+            float acc = cc[0] * (float)c0[gx - hx - hy * st];
+#pragma GCC unroll 64
+            for (int k = 1; k < SX * SY; ++k) acc = acc + cc[k] * (float)c0[gx + (k % SX - hx) + (k / SX - hy) * st];
+            if (add_f) acc = acc + add_v;
+            orow[gx] = sizeof(TO) == 4 ? (TO)acc : (TO)(int)acc;
         }
         for (int gx = x_hi; gx < W; ++gx) border(gx);
     }

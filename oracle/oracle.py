@@ -23,6 +23,7 @@ from hipacc_b200 import masks as M
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _EMIT_PATH = os.path.join(HERE, "liboracle_emitcpu.so")
+_FAST_PATH = os.path.join(HERE, "liboracle_emitcpu_fast.so")
 _REF_PATH = os.path.join(HERE, "_ref", "libhipacc_ref.so")
 
 
@@ -33,6 +34,7 @@ def build(force=False):
 
 
 _emit = None
+_fast = None
 _ref = None
 
 
@@ -49,6 +51,17 @@ def emit_lib():
         _emit.oc_binning.argtypes = [C.POINTER(A.hb_binning_desc), C.POINTER(C.c_uint)]
         _emit.oc_reduce_minmaxsum_f32.argtypes = [C.POINTER(A.hb_view), C.POINTER(C.c_float), C.POINTER(C.c_double)]
     return _emit
+
+
+def fast_lib():
+    """oracle/liboracle_emitcpu_fast.so: the specialised (-emit-cpu shaped) loops of the TIMED CPU leg (emit_cpu_fast.cpp)"""
+    global _fast
+    if _fast is None:
+        if not os.path.exists(_FAST_PATH):
+            build()
+        _fast = C.CDLL(_FAST_PATH)
+        _fast.ocf_local_op.argtypes = [C.POINTER(A.hb_local_desc)]
+    return _fast
 
 
 def have_ref():
@@ -75,6 +88,7 @@ def num_threads():
 
 def set_num_threads(n):
     emit_lib().oc_set_num_threads(int(n))
+    fast_lib().ocf_set_num_threads(int(n))
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -107,6 +121,18 @@ def local_op(spec: S.LocalSpec, img, out=None, roi_in=None, roi_out=None, ghost=
     d.in_ = np_view(img, roi_in, ghost)
     d.out = np_view(out, roi_out)
     _check(emit_lib().oc_local_op(C.byref(d)), "local_op")
+    return out
+
+
+def local_op_fast(spec: S.LocalSpec, img, out=None, roi_in=None, roi_out=None, ghost=(0, 0)):
+    """The same operator through the specialised CPU loops (emit_cpu_fast.cpp); raises when no specialisation exists."""
+    if out is None:
+        out = np.zeros(img.shape, dtype=A.DTYPE_NUMPY[spec.out_dtype])
+    d = A.hb_local_desc()
+    spec.fill(d)
+    d.in_ = np_view(img, roi_in, ghost)
+    d.out = np_view(out, roi_out)
+    _check(fast_lib().ocf_local_op(C.byref(d)), "local_op_fast")
     return out
 
 

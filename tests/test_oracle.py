@@ -377,3 +377,35 @@ def test_synth_numpy_equals_torch():
     full = synth.image_np("float32", 16, 32, seed=1)
     strip = synth.image_np("float32", 16, 8, seed=1, y0=8)
     np.testing.assert_array_equal(full[8:16], strip)
+
+
+# ------------------------------------------------------------------ the TIMED CPU leg (oracle/emit_cpu_fast.cpp)
+@pytest.mark.parametrize("b", [A.CLAMP, A.REPEAT, A.MIRROR, A.CONSTANT, A.UNDEFINED])
+@pytest.mark.parametrize("shape", [(39, 66), (1, 1), (2, 3), (131, 257), (64, 1031)])
+def test_fast_cpu_leg_equals_generic_oracle(oracle, b, shape):
+    """The specialised loops bench.py times on the host (constexpr masks, interior / border split, AVX2) are the SAME
+    function as the generic checker: bit-for-bit on ragged sizes, every boundary mode, ROIs and ghost rows."""
+    h, w = shape
+    f = synth.image_np("float32", w, h, seed=71)
+    u = synth.image_np("uint8", w, h, seed=72)
+    f32_specs = [S.domain_reduce_f32(m.astype(np.float32), b, const=0.25) for m in (M.SOBEL3_X, M.SOBEL3_Y, M.LAPLACE3, np.array([[0, 1, 0], [1, -4, 1], [0, 1, 0]]))]
+    f32_specs += [S.convolve_f32(M.GAUSS[sz], b, const=0.25) for sz in (3, 5, 7)]
+    f32_specs += [S.convolve_f32(M.SOBEL3_X.astype(np.float32), b, const=0.25)]   # convolve() visits the zero taps too
+    for spec in f32_specs:
+        np.testing.assert_array_equal(oracle.local_op_fast(spec, f), oracle.local_op(spec, f))
+    for sz in (3, 5, 7):
+        spec = S.gaussian_blur(M.GAUSS[sz], b)
+        np.testing.assert_array_equal(oracle.local_op_fast(spec, u), oracle.local_op(spec, u))
+    if h > 20 and w > 40:   # ROI + crop accessor + ghost rows
+        roi_in, roi_out, ghost = (w - 9, h - 12, 4, 6), (w - 9, h - 12, 5, 3), (2, 3)
+        for spec in (f32_specs[0], f32_specs[5]):
+            o1, o2 = np.zeros_like(f), np.zeros_like(f)
+            oracle.local_op(spec, f, out=o1, roi_in=roi_in, roi_out=roi_out, ghost=ghost)
+            oracle.local_op_fast(spec, f, out=o2, roi_in=roi_in, roi_out=roi_out, ghost=ghost)
+            np.testing.assert_array_equal(o1, o2)
+
+
+def test_fast_cpu_leg_refuses_what_it_does_not_specialise(oracle):
+    u = synth.image_np("uint8", 40, 30, seed=73)
+    with pytest.raises(RuntimeError):
+        oracle.local_op_fast(S.sobel_u8(M.SOBEL3_X), u)          # integer accumulate: generic checker only
