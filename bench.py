@@ -14,9 +14,16 @@ Timed on the device with CUDA events on the stream the kernels run on, after W >
 barrier + synchronize on both sides, max over ranks.  Inputs (256 MiB) and outputs (768 MiB) are
 larger than the 126 MB L2, so no explicit flush is needed (stated in `config`).
 
---impl reference: the reference's CPU path for the same workload (the restated -emit-cpu code in
-oracle/, all host threads; the Hipacc compiler itself cannot be built here -- DESIGN.md) on a bounded
-sample.  Rank 0 only.
+Every run also reports, under "operators", the two sharded configs BASELINE.json names: C4 (fused Harris on a
+32768 x 32768 uchar image) and C5 (8-level Gaussian / Laplacian pyramid of a 16384 x 16384 float image).  At N > 1 the
+named image is cut into N row strips (STRONG scaling; peer-to-peer halo exchange / all-gather inside the timed step),
+every rank also runs the unsharded operator on the whole image on its own GPU, checks its strip bit for bit against it
+("sharded_parity") and times it ("strong_efficiency" = T(1 GPU) / (N * T(N GPUs)), both measured in this run).
+
+--impl reference: the reference's CPU path for the same workload -- the -emit-cpu shaped loops in
+oracle/emit_cpu_fast.cpp (constexpr masks, interior / border split, AVX2; bit-identical to the generic checker
+oracle/emit_cpu.cpp; the Hipacc compiler itself cannot be built here -- DESIGN.md), all host threads, the FULL
+8192 x 8192 image per step.  Rank 0 only: under torchrun the same host CPU is timed at every N.
 """
 import argparse
 import json
@@ -98,25 +105,37 @@ def specs_for_workload():
 
 
 # --------------------------------------------------------------------------------------- CPU legs
-def cpu_baseline(rows, repeats=3):
-    """The oracle ("port" of -emit-cpu, oracle/emit_cpu.cpp) on the host cores: the three operators on a
-    W x rows sample of the same synthetic image.  Returns (Gpx/s, cores, sample description)."""
+def _cpu_step_fn():
+    """One CPU step = the three operators over the FULL 8192 x 8192 image (the GPU arm's per-GPU workload), through the
+    specialised -emit-cpu shaped loops (oracle/emit_cpu_fast.cpp, pinned bit-for-bit against the generic oracle)."""
     import numpy as np
     from hipacc_b200 import synth
     from oracle import oracle as O
-    O.set_num_threads(len(os.sched_getaffinity(0)))
-    img = synth.image_np("float32", W, rows, seed=2)
+    O.set_num_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
+    img = synth.image_np("float32", W, H, seed=2)
     specs = specs_for_workload()
     outs = [np.empty_like(img) for _ in specs]
-    for s, o in zip(specs, outs):   # warm-up (page faults, OpenMP pool)
-        O.local_op(s, img, out=o)
+
+    def step():
+        for s, o in zip(specs, outs):
+            O.local_op_fast(s, img, out=o)
+    return step, O.num_threads(), len(specs)
+
+
+CPU_SAMPLE = (f"3 operators on the full {W}x{H} float image per step (same config as the GPU arm at N = 1), -emit-cpu shaped loops: "
+              "constexpr masks, interior / border split, g++ -O3 AVX2 without FMA contraction, OpenMP over rows")
+
+
+def cpu_baseline(repeats=3):
+    """-> (Gpx/s, cores, sample description); best of `repeats` after one warm-up step"""
+    step, cores, nops = _cpu_step_fn()
+    step()   # warm-up (page faults, OpenMP pool)
     best = float("inf")
     for _ in range(repeats):
         t = time.perf_counter()
-        for s, o in zip(specs, outs):
-            O.local_op(s, img, out=o)
+        step()
         best = min(best, time.perf_counter() - t)
-    return len(specs) * W * rows / best / 1e9, O.num_threads(), f"3 operators on {W}x{rows} float rows of the same image, best of {repeats}"
+    return nops * W * H / best / 1e9, cores, CPU_SAMPLE + f", best of {repeats}"
 
 
 def run_reference(args):
@@ -124,35 +143,48 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(1, args.warmup)
-    import numpy as np
-    from hipacc_b200 import synth
-    from oracle import oracle as O
-    O.set_num_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
-    rows = 4096   # bounded sample: half of the image per step
-    img = synth.image_np("float32", W, rows, seed=2)
-    specs = specs_for_workload()
-    outs = [np.empty_like(img) for _ in specs]
-
-    def step():
-        for s, o in zip(specs, outs):
-            O.local_op(s, img, out=o)
+    step, cores, nops = _cpu_step_fn()
     for _ in range(warm):
         step()
     t = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t) / steps
-    val = len(specs) * W * rows / dt / 1e9
-    cores = O.num_threads()
-    sample = f"{W}x{rows} float rows per step (half of the 8192x8192 image), restated -emit-cpu code, OpenMP {cores} threads"
+    val = nops * W * H / dt / 1e9
+    sample = CPU_SAMPLE + f", OpenMP {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gpixels/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: Sobel-X + Sobel-Y + Laplace 3x3 float 8192x8192 MIRROR (CPU sample)", "sample": sample},
+        "config": {"workload": "C2: Sobel-X + Sobel-Y + Laplace 3x3 local operators, float 8192x8192, MIRROR boundary (CPU arm)", "sample": sample,
+                   "note": "the CPU arm does not scale with --gpus: rank 0 times the same host cores on one 8192x8192 image at every N"},
         "cpu_baseline": {"value": val, "unit": "Gpixels/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def measured_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel whose name contains `kernel_substr`, from the
+    newest committed ncu launch list (profiles/*launches*.csv, `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
+    dram__bytes_write.sum`); None when no list carries the metric.  -> (bytes per launch, source file)"""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*launches*.csv")), key=lambda f: (os.path.basename(f).split("_")[0], os.path.getmtime(f)))
+    for path in reversed(files):
+        try:
+            per_id = {}
+            with open(path, newline="") as fh:
+                rows = [r for r in csv.reader(l for l in fh if l.startswith('"'))]
+            hdr = rows[0]
+            iK, iM, iV, iI = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+            for r in rows[1:]:
+                if kernel_substr in r[iK] and r[iM] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    per_id[r[iI]] = per_id.get(r[iI], 0.0) + float(r[iV].replace(",", ""))
+            if per_id:
+                return sum(per_id.values()) / len(per_id), os.path.relpath(path, ROOT)
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -169,6 +201,8 @@ def main():
     ap.add_argument("--e2e-blocking", action="store_true", help="time the end-to-end leg with the blocking hb_image_write / hb_image_read calls (the reference's API shape) instead of the pipelined async region copies")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: run the halo kernel in stream order instead of overlapping it with the first operator's interior rows")
     ap.add_argument("--no-graph", action="store_true", help="launch every operator from the host instead of replaying a CUDA graph of one step")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded bit comparison (tuning sweeps only)")
+    ap.add_argument("--no-named", action="store_true", help="skip the C4 / C5 entries of 'operators' (tuning sweeps only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -312,12 +346,7 @@ def main():
                 "traffic": None, "kernel": "local_tma_f32_kernel<3,3,Mask*> (TMA-staged, one 128x32 tile per CTA)",
                 "note": "frac can slightly exceed 1: consecutive operators re-read the same 256 MiB input and a part of it still sits in the 126 MB L2; single-operator launches reach 0.95 (operators.C2_*)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_PX * W * plan.rows, "avg_launch_ms": per_launch_ms}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("local_tiled_f32_3x3_bytes_per_launch")
-        except Exception:
-            pass
+    roofline["traffic"], roofline["traffic_source"] = measured_traffic("local_tma_f32_kernel<3, 3")
 
     # ---- e2e: the same step through the C-ABI memory calls with HOST (pinned) buffers, copies inside the timed region
     L = hb.lib()
@@ -403,14 +432,40 @@ def main():
            "api": ("hb_image_write + 3 x hb_local_op + 3 x hb_image_read (blocking calls, pinned host buffers)" if args.e2e_blocking else
                    "8 row strips: hb_image_write_region_async -> 3 x hb_local_op -> 3 x hb_image_read_region_async on three streams (pinned host buffers; every byte crosses PCIe inside the timed region)")}
 
+    # ---- sharded parity of the headline step (outside the timed region): every rank recomputes the three operators
+    # UNSHARDED on the whole global image on its own GPU and compares its strip bit for bit
+    parity = {}
+    if world > 1 and not args.no_parity:
+        step_direct()
+        torch.cuda.synchronize()
+        whole = hb.empty_image(A.F32, W, H * world, device=dev)
+        for r in range(world):   # counter-based generator: any rank can produce any rows of the global image
+            whole[r * H:(r + 1) * H].copy_(synth.image_torch("float32", W, H, seed=2, y0=r * H, device=dev))
+        ref_out = hb.empty_image(A.F32, W, H * world, device=dev)
+        ok = True
+        for s_, o in zip(specs, outs):
+            hb.local_op(s_, whole, dst=ref_out, stream=stream)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(o[plan.ghost_top:plan.ghost_top + plan.rows], ref_out[plan.y0:plan.y1])
+        parity["C2"] = ok
+        del whole, ref_out
+
+    operators = named_operators(hb, dev, world, rank, stream, halo is not None, peak, parity, args)
     if args.extra:
-        operators = extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream, halo is not None)
-    else:
-        operators = None
+        operators.update(extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream, halo is not None))
+
+    sharded_parity = None
+    if world > 1 and parity:
+        flags = torch.tensor([1 if all(parity.values()) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        mine = ", ".join(f"{k}:{'ok' if v else 'MISMATCH'}" for k, v in parity.items())
+        if not all(parity.values()):
+            sys.stderr.write(f"[rank {rank}] sharded parity FAILED: {mine}\n")
+        sharded_parity = "ok" if int(flags.item()) else "MISMATCH"
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_baseline(rows=4096)
+        v, cores, sample = cpu_baseline()
         cpu = {"value": v, "unit": "Gpixels/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
@@ -428,16 +483,184 @@ def main():
         }
         if operators:
             line["operators"] = operators
+        if world > 1:
+            line["sharded_parity"] = sharded_parity if sharded_parity else "not run"
+            line["sharded_parity_detail"] = ("every rank ran the unsharded operator on the whole global image on its own GPU and compared its strip bit for bit: "
+                                             + ", ".join(sorted(parity)) if parity else "skipped (--no-parity)")
         print(json.dumps(line))
     if world > 1:
-        if halo is not None and rank == 0:
+        if halo is not None:   # every rank: a timed-out exchange poisons its control block
             n_ex, timed_out = halo.status()
-            if timed_out:
-                sys.stderr.write("WARNING: a halo exchange timed out waiting for a neighbour\n")
+            if timed_out or n_ex < 0:
+                sys.stderr.write(f"[rank {rank}] ERROR: a halo exchange timed out waiting for a neighbour; results of this run are invalid\n")
         sys.stdout.flush()
         torch.cuda.synchronize()
         dist.barrier()
         os._exit(0)   # skip interpreter teardown: CUDA graphs / IPC mappings and the NCCL communicator do not need an orderly exit
+
+
+def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
+    """The two sharded configs BASELINE.json names, at every N: C4 = fused Harris on a 32768 x 32768 uchar image, C5 =
+    8-level Gaussian / Laplacian pyramid of a 16384 x 16384 float image.  N = 1: the whole image on the GPU.  N > 1:
+    STRONG scaling -- the same image cut into N row strips (halo exchange / all-gather peer to peer inside the timed
+    step); every rank additionally runs the unsharded operator on the whole image on its own GPU, compares its strip
+    bit for bit (parity[...]) and times it, so strong_efficiency = T(1) / (N * T(N)) comes from one run."""
+    import torch
+    import torch.distributed as dist
+    from hipacc_b200 import _abi as A, masks as M, strips, synth
+    res = {}
+    if args.no_named:
+        return res
+
+    def timeit(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def graphed(fn):
+        """capture fn into a CUDA graph (every rank falls back together) -> (callable, how)"""
+        fn()
+        torch.cuda.synchronize()
+        ok = 1
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                fn()
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            sys.stderr.write(f"[rank {rank}] graph capture failed: {e}\n")
+        if world > 1:
+            t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+            ok = int(t_ok.item())
+        return (g.replay, "CUDA graph replay") if ok else (fn, "direct launches")
+
+    # ------------------------------------------------------------------ C4: Harris 32768 x 32768 uchar
+    Wc = Hc = 32768
+    whole = hb.empty_image(A.U8, Wc, Hc, device=dev)
+    for y in range(0, Hc, 4096):
+        whole[y:y + 4096].copy_(synth.image_torch("uint8", Wc, 4096, seed=4, y0=y, device=dev))
+    whole_out = hb.empty_image(A.U8, Wc, Hc, device=dev)
+    t1 = timeit(lambda: hb.harris(whole, dst=whole_out, stream=stream), reps=5, warm=2)
+    entry = {"Gpx_s": Wc * Hc / (t1 * 1e-3) / 1e9, "ms": t1, "n_gpus": world, "alg_GB_s": 2 * Wc * Hc / (t1 * 1e-3) / 1e9,
+             "hbm_frac": 2 * Wc * Hc / (t1 * 1e-3) / 1e9 / peak, "note": "fused 9-kernel pipeline, one launch; integer-issue bound"}
+    if world > 1:
+        plan = strips.StripPlan(Wc, Hc, world, rank, radius=2, boundary=A.CLAMP)
+        buf = hb.alloc_image(A.U8, Wc, plan.buffer_rows, device=dev)
+        strips.owned(buf, plan).copy_(whole[plan.y0:plan.y1])
+        out = torch.zeros_like(buf)
+        halo = strips.P2PHalo(hb, buf, plan) if p2p else None
+
+        def harris_step():
+            if halo is not None:
+                halo.exchange(stream)
+            else:
+                strips.exchange_halos(buf, plan)
+            hb.harris(buf, dst=out, roi=plan.roi(), ghost=plan.ghost(), stream=stream)
+        harris_step()
+        torch.cuda.synchronize()
+        if not args.no_parity:
+            parity["C4"] = bool(torch.equal(strips.owned(out, plan), whole_out[plan.y0:plan.y1]))
+        fn, how = graphed(harris_step) if p2p else (harris_step, "direct launches")
+        tn = max_over_ranks(timeit(fn, reps=10, warm=3))
+        entry = {"Gpx_s": Wc * Hc / (tn * 1e-3) / 1e9, "ms": tn, "n_gpus": world, "launch": how, "single_gpu_ms": t1,
+                 "strong_efficiency": t1 / (world * tn),
+                 "note": f"strong scaling: {plan.rows} rows per rank + 2 ghost rows pushed per step (" + ("peer-to-peer kernel" if p2p else "NCCL send/recv")
+                         + "); single_gpu_ms = the unsharded 32768^2 image on this rank's GPU in the same run"}
+        if halo is not None:
+            halo.check()
+        del buf, out
+    res["C4_harris_32768x32768"] = entry
+    del whole, whole_out
+
+    # ------------------------------------------------------------------ C5: pyramid, 8 levels, 16384 x 16384 float
+    Wp = Hp = 16384
+    depth = 8
+    n = Wp * Hp
+    img = hb.empty_image(A.F32, Wp, Hp, device=dev)
+    for y in range(0, Hp, 2048):
+        img[y:y + 2048].copy_(synth.image_torch("float32", Wp, 2048, seed=5, y0=y, device=dev))
+    pg = hb.Pyramid(img, depth)
+    pl = hb.Pyramid(hb.empty_image(A.F32, Wp, Hp, device=dev).zero_(), depth)
+    sp = None
+    if world > 1:   # sharded traversal first (its parity reference is the FIRST unsharded traversal of the same input)
+        plan = strips.PyramidShardPlan(Wp, Hp, depth, world, rank, 5)
+        sp = strips.ShardedPyramid(plan, dev, hb=hb if p2p else None)
+        if p2p:
+            sp.enable_p2p(hb)
+        sp.owned(sp.gaus, 0).copy_(img[plan.y0(0):plan.y1(0)])
+
+        def traverse():
+            if p2p:
+                sp.traverse(hb, M.GAUSS5, stream=stream)
+            else:   # NCCL fallback: send/recv for the level-0 halo, all-gather for level G
+                strips.exchange_halos(sp.gaus[0], sp.strip0_plan())
+                sp.down_sharded(hb, M.GAUSS5, stream)
+                G = plan.G
+                dist.all_gather_into_tensor(sp.gaus[G], sp.gaus[G][plan.y0(G):plan.y1(G)].contiguous())
+                sp.coarse_and_up(hb, M.GAUSS5, stream)
+        traverse()
+        torch.cuda.synchronize()
+    hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream)
+    torch.cuda.synchronize()
+    if sp is not None and not args.no_parity:
+        ok = True
+        for l in range(depth):
+            y0, y1 = plan.y0(l), plan.y1(l)
+            ok = ok and torch.equal(sp.owned(sp.gaus, l), pg.levels[l][y0:y1]) and torch.equal(sp.owned(sp.lap, l), pl.levels[l][y0:y1])
+        parity["C5"] = bool(ok)
+    with hb.Graph(stream) as g:                      # hb_graph_begin / hb_graph_end: the 14 level kernels as one launch
+        hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream)
+    t1 = timeit(lambda: g.launch(), reps=5, warm=2)
+    g.destroy()
+    alg = int(23 * n * 4 / 3)
+    entry = {"Gpx_s": n / (t1 * 1e-3) / 1e9, "ms": t1, "n_gpus": world, "alg_GB_s": alg / (t1 * 1e-3) / 1e9, "hbm_frac": alg / (t1 * 1e-3) / 1e9 / peak,
+             "note": "fused down (blur+subsample+DoG) 9n + fused up (Restore+Blend) 14n bytes per transition; 14 kernels replayed as one hb_graph launch"}
+    if sp is not None:
+        fn, how = graphed(traverse) if p2p else (traverse, "direct launches")
+        tn = max_over_ranks(timeit(fn, reps=5, warm=2))
+        entry = {"Gpx_s": n / (tn * 1e-3) / 1e9, "ms": tn, "n_gpus": world, "launch": how, "single_gpu_ms": t1, "strong_efficiency": t1 / (world * tn),
+                 "note": f"strong scaling: ONE level-0 halo exchange ({plan.E0} rows per neighbour) + ONE all-gather of level {plan.G} "
+                         f"({Wp >> plan.G}x{Hp >> plan.G}) per traversal, levels >= {plan.G} replicated, extension rows recomputed instead of exchanged; "
+                         "single_gpu_ms = the unsharded traversal on this rank's GPU in the same run"}
+        if os.environ.get("HB_BENCH_PHASES") and p2p:   # diagnosis: device time of the traversal's phases (direct launches)
+            names = ["exchange0", "down_sharded", "gather", "coarse_and_up"]
+            acc = [0.0] * 4
+            for _ in range(6):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                dist.barrier()
+                ev[0].record(stream)
+                sp.halo0.exchange(stream); ev[1].record(stream)
+                sp.down_sharded(hb, M.GAUSS5, stream); ev[2].record(stream)
+                sp.gatherG.gather(stream); ev[3].record(stream)
+                sp.coarse_and_up(hb, M.GAUSS5, stream); ev[4].record(stream)
+                torch.cuda.synchronize()
+                for i in range(4):
+                    acc[i] += ev[i].elapsed_time(ev[i + 1]) / 6
+            sys.stderr.write(f"[rank {rank}] C5 phases (ms): " + ", ".join(f"{n_} {a_:.3f}" for n_, a_ in zip(names, acc)) + "\n")
+        if sp.halo0 is not None:
+            sp.halo0.check()
+        if sp.gatherG is not None:
+            sp.gatherG.check()
+    res["C5_pyramid8_16384"] = entry
+    return res
 
 
 def extra_operators(hb, dev, peak):
@@ -507,27 +730,18 @@ def extra_operators(hb, dev, peak):
     entry("C4_harris_fused_u8_32768x4096", 32768 * 4096, 2 * 32768 * 4096, timeit(lambda: hb.harris(hs, dst=ho, stream=stream), reps=5),
           "fused 9-kernel pipeline, integer-issue bound")
     del hs, ho
-    # C5 pyramid 8 levels float 16384^2
-    base = hb.empty_image(A.F32, 16384, 16384, device=dev)
-    base.copy_(synth.image_torch("float32", 16384, 16384, seed=5, device=dev))
-    pg = hb.Pyramid(base, 8)
-    pl = hb.Pyramid(hb.empty_image(A.F32, 16384, 16384, device=dev).zero_(), 8)
-    hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream)
-    torch.cuda.synchronize()
-    with hb.Graph(stream) as g:                      # hb_graph_begin / hb_graph_end: the 14 level kernels as one launch
-        hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=stream)
-    ms = timeit(lambda: g.launch(), reps=5, warm=2)
-    g.destroy()
-    n = 16384 * 16384
-    entry("C5_pyramid8_f32_16384", n, int(23 * n * 4 / 3), ms,
-          "fused down (blur+subsample+DoG) 9n + fused up (Restore+Blend) 14n bytes per transition; 14 kernels replayed as one hb_graph launch")
+    # Reduction_Sum sample: int 4096 x 4096 (vectorised integer kernel, IDP-free for 32-bit pixels)
+    it = torch.randint(-100, 100, (4096, 4096), dtype=torch.int32, device=dev)
+    entry("reduce_sum_s32_4096", 4096 * 4096, 4 * 4096 * 4096, timeit(lambda: hb.reduce(it, A.SUM, stream=stream)), "blocking call incl. the 16-byte result read-back")
+    u8r = torch.randint(0, 255, (8192, 8192), dtype=torch.uint8, device=dev)
+    entry("reduce_sum_u8_8192", 8192 * 8192, 8192 * 8192, timeit(lambda: hb.reduce(u8r, A.SUM, stream=stream)), "IDP.4A byte sums; blocking call incl. read-back")
     return res
 
 
 def extra_sharded(hb, dev, world, rank, stream, p2p=True):
-    """N > 1: the sharded BASELINE configs (strong scaling: the named global image cut into `world` row strips).
-    C4 Harris 32768^2 uchar (halo exchange + fused kernel per step), C5 pyramid 16384^2 float, 8 levels (one halo
-    exchange per level transition), C3 fused min/max/sum + one all-reduce per scalar.  Device-timed, max over ranks."""
+    """N > 1 extras: the FIRST sharded-pyramid design for comparison (one halo exchange per level transition: 14 exchange
+    launches per traversal; the default line times the one-exchange + one-all-gather design) and the C3 reductions
+    (per-rank fused min/max/sum + one all-gather of the partials).  Device-timed, max over ranks."""
     import torch
     import torch.distributed as dist
     from hipacc_b200 import _abi as A, masks as M, strips, synth
@@ -565,25 +779,6 @@ def extra_sharded(hb, dev, world, rank, stream, p2p=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # C4: Harris on a 32768 x 32768 uchar image, `world` row strips with 2 ghost rows
-    Wc, Hc = 32768, 32768
-    plan = strips.StripPlan(Wc, Hc, world, rank, radius=2, boundary=A.CLAMP)
-    buf = hb.alloc_image(A.U8, Wc, plan.buffer_rows, device=dev)
-    strips.owned(buf, plan).copy_(synth.image_torch("uint8", Wc, plan.rows, seed=4, y0=plan.y0, device=dev))
-    out = torch.empty_like(buf)
-    halo = strips.P2PHalo(hb, buf, plan) if p2p else None
-
-    def harris_step():
-        if halo is not None:
-            halo.exchange(stream)
-        else:
-            strips.exchange_halos(buf, plan)
-        hb.harris(buf, dst=out, roi=plan.roi(), ghost=plan.ghost(), stream=stream)
-    fn, how = graphed(harris_step) if p2p else (harris_step, "direct launches")
-    ms = timeit(fn)
-    res["C4_harris_fused_u8_32768x32768_sharded"] = {"Gpx_s": Wc * Hc / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world, "launch": how,
-                                                      "note": f"strong scaling: {plan.rows} rows per rank + 2 ghost rows exchanged per step (" + ("peer-to-peer push kernel" if p2p else "NCCL send/recv") + ")"}
-    del buf, out
     # C5: 8-level pyramid of a 16384 x 16384 float image on row strips
     Wp = Hp = 16384
     pg = strips.StripPyramid(Wp, Hp, 8, world, rank, radius=4, device=dev, hb=hb)
@@ -595,7 +790,7 @@ def extra_sharded(hb, dev, world, rank, stream, p2p=True):
     traverse = lambda: strips.pyramid_traverse_strips(hb, pg, pl, M.GAUSS5, stream=stream)  # noqa: E731
     fn, how = graphed(traverse) if p2p else (traverse, "direct launches")
     ms = timeit(fn, reps=3, warm=1)
-    res["C5_pyramid8_f32_16384_sharded"] = {"Gpx_s": Wp * Hp / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world, "launch": how,
+    res["C5_pyramid8_f32_16384_sharded_exchange_per_level"] = {"Gpx_s": Wp * Hp / (ms * 1e-3) / 1e9, "ms": ms, "n_gpus": world, "launch": how,
                                             "note": "strong scaling: 14 halo exchange launches (4 rows per neighbour, " + ("peer-to-peer push kernels" if p2p else "NCCL send/recv") + ") + 14 fused level kernels per traversal"}
     del pg, pl
     # C3 reductions: per-rank fused min/max/sum partials + all-reduce (weak: 8192 x 8192 per rank)

@@ -73,6 +73,7 @@ def lib():
         L.hb_halo_status.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.hb_halo_exchange.argtypes = [C.POINTER(A.hb_halo_desc), C.c_void_p]
         L.hb_halo_exchange_batch.argtypes = [C.POINTER(C.POINTER(A.hb_halo_desc)), C.c_int, C.c_void_p]
+        L.hb_allgather_rows.argtypes = [C.POINTER(A.hb_gather_desc), C.c_void_p]
         _lib = L
     return _lib
 

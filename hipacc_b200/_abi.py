@@ -117,6 +117,20 @@ class hb_halo_desc(C.Structure):
     ]
 
 
+HB_MAX_PEERS = 15
+
+
+class hb_gather_desc(C.Structure):
+    _fields_ = [
+        ("buf", C.c_void_p), ("pitch_bytes", C.c_size_t), ("row_bytes", C.c_size_t),
+        ("row0", C.c_int), ("rows", C.c_int),
+        ("ctrl", C.c_void_p),
+        ("my_slot", C.c_int), ("n_peers", C.c_int),
+        ("peer_buf", C.c_void_p * HB_MAX_PEERS), ("peer_ctrl", C.c_void_p * HB_MAX_PEERS),
+        ("peer_slot", C.c_int * HB_MAX_PEERS),
+    ]
+
+
 def make_view(ptr, dtype, img_w, img_h, stride=None, roi=None, ghost=(0, 0)):
     """Build an hb_view.  roi = (w, h, ox, oy) or None for the whole image."""
     v = hb_view()
@@ -142,5 +156,5 @@ EXPORTS = [
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",
     "hb_harris", "hb_pyr_down", "hb_pyr_up",
-    "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange", "hb_halo_exchange_batch",
+    "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange", "hb_halo_exchange_batch", "hb_allgather_rows",
 ]

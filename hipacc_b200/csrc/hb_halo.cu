@@ -48,15 +48,37 @@ __device__ __forceinline__ bool spin_until(int *flag, int want) {
     return true;
 }
 
-__device__ __forceinline__ void push_rows(unsigned char *dst, size_t dpitch, const unsigned char *src, size_t spitch, size_t row_bytes, int rows) {
+// copy `rows` rows of `row_bytes` bytes into peer memory.  The CTAs of one exchange share the work: CTA `part` of
+// `nparts` takes every nparts-th chunk of 16-byte vectors; each thread has 8 independent loads in flight before its
+// first remote store (a dependent load -> store loop moves ~16 KB per microsecond and CTA, NVLink wants megabytes in flight).
+__device__ __forceinline__ void push_rows(unsigned char *dst, size_t dpitch, const unsigned char *src, size_t spitch, size_t row_bytes, int rows,
+                                          int part, int nparts) {
     if ((row_bytes | dpitch | spitch | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0) {
-        const size_t vpr = row_bytes / 16;
-        for (size_t i = threadIdx.x; i < vpr * rows; i += blockDim.x) {
-            const size_t r = i / vpr, c = i - r * vpr;
-            reinterpret_cast<uint4 *>(dst + r * dpitch)[c] = reinterpret_cast<const uint4 *>(src + r * spitch)[c];
+        constexpr int U = 8;
+        const size_t vpr = row_bytes / 16, total = vpr * rows;
+        const size_t step = (size_t)blockDim.x * U;
+        for (size_t base = (size_t)part * step; base < total; base += step * nparts) {
+            uint4 v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const size_t i = base + (size_t)k * blockDim.x + threadIdx.x;
+                if (i < total) {
+                    const size_t r = i / vpr, c = i - r * vpr;
+                    v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + r * spitch) + c);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const size_t i = base + (size_t)k * blockDim.x + threadIdx.x;
+                if (i < total) {
+                    const size_t r = i / vpr, c = i - r * vpr;
+                    reinterpret_cast<uint4 *>(dst + r * dpitch)[c] = v[k];
+                }
+            }
         }
     } else {
-        for (size_t i = threadIdx.x; i < row_bytes * rows; i += blockDim.x) {
+        const size_t total = row_bytes * rows;
+        for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < total; i += (size_t)blockDim.x * nparts) {
             const size_t r = i / row_bytes, c = i - r * row_bytes;
             dst[r * dpitch + c] = src[r * spitch + c];
         }
@@ -75,16 +97,22 @@ struct HaloBatch {
 // silently.  The kernel then raises ctrl[5], skips the push / publish steps and POISONS the exchange counter (negative),
 // so every later exchange on this control block returns immediately and hb_halo_status reports the failure.
 constexpr int kPoisoned = -(1 << 30);
+constexpr int HALO_THREADS = 512;
 
-__global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_constant__ HaloBatch batch) {
+// grid = (buffers of the batch, parts): the `parts` CTAs of a buffer all wait for the neighbours' acks (read-only
+// polling), push their share of the rows, and the LAST one to finish (ticket in ctrl[6]) publishes the data, waits for
+// the neighbours' rows and advances the exchange counter -- every CTA has read the counter before that can happen.
+__global__ void __launch_bounds__(HALO_THREADS) halo_exchange_kernel(const __grid_constant__ HaloBatch batch) {
     const HaloParams &p = batch.p[blockIdx.x];
+    const int part = blockIdx.y, nparts = gridDim.y;
     __shared__ int ok;
-    const int e = p.ctrl[0];   // read by every thread before thread 0 advances it (barriers below)
+    const int e = p.ctrl[0];
     if (e < 0) return;         // poisoned by an earlier timeout
     if (threadIdx.x == 0) {
-        // my ghost rows of exchange e-1 are consumed: the neighbours may overwrite them
-        if (p.up_ctrl) st_release_sys(p.up_ctrl + 4, e);      // I am the upper neighbour's lower neighbour
-        if (p.down_ctrl) st_release_sys(p.down_ctrl + 3, e);
+        if (part == 0) {       // my ghost rows of exchange e-1 are consumed: the neighbours may overwrite them
+            if (p.up_ctrl) st_release_sys(p.up_ctrl + 4, e);      // I am the upper neighbour's lower neighbour
+            if (p.down_ctrl) st_release_sys(p.down_ctrl + 3, e);
+        }
         bool good = true;
         if (p.up_ctrl) good = spin_until(p.ctrl + 3, e) && good;
         if (p.down_ctrl) good = spin_until(p.ctrl + 4, e) && good;
@@ -92,13 +120,18 @@ __global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_consta
     }
     __syncthreads();
     if (ok) {
-        if (p.up_dst) push_rows(p.up_dst, p.up_pitch, p.buf + (size_t)p.gt * p.pitch, p.pitch, p.row_bytes, p.R);
-        if (p.down_dst) push_rows(p.down_dst, p.down_pitch, p.buf + (size_t)(p.gt + p.rows - p.R) * p.pitch, p.pitch, p.row_bytes, p.R);
+        if (p.up_dst) push_rows(p.up_dst, p.up_pitch, p.buf + (size_t)p.gt * p.pitch, p.pitch, p.row_bytes, p.R, part, nparts);
+        if (p.down_dst) push_rows(p.down_dst, p.down_pitch, p.buf + (size_t)(p.gt + p.rows - p.R) * p.pitch, p.pitch, p.row_bytes, p.R, part, nparts);
         __threadfence_system();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        bool good = ok != 0;
+        if (!ok) atomicExch(p.ctrl + 5, 1);
+        __threadfence();
+        if (atomicAdd(reinterpret_cast<unsigned *>(p.ctrl + 6), 1u) != (unsigned)nparts - 1) return;   // not the last CTA of this buffer
+        p.ctrl[6] = 0;
+        __threadfence();
+        bool good = atomicAdd(p.ctrl + 5, 0) == 0;
         if (good) {
             if (p.up_ctrl) st_release_sys(p.up_ctrl + 2, e + 1);   // data from its lower neighbour
             if (p.down_ctrl) st_release_sys(p.down_ctrl + 1, e + 1);
@@ -112,6 +145,64 @@ __global__ void __launch_bounds__(1024) halo_exchange_kernel(const __grid_consta
             p.ctrl[0] = kPoisoned;
         }
         __threadfence();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// All-gather of row strips over peer memory: every rank owns rows [row0, row0 + rows) of an image that all ranks keep
+// in FULL (the coarse pyramid levels, small enough to replicate) and pushes them into the same rows of every peer's
+// copy.  One CTA per peer: CTA j handshakes with peer j alone (ack: "your rows of the previous gather are consumed",
+// push, publish, wait for its rows), so the peers proceed independently; the last CTA to finish advances the
+// gather counter.  Control block (ints): [0] gathers completed, [1] ticket, [5] timeout flag,
+// [8 + slot] ack from rank `slot`, [24 + slot] data from rank `slot`, [40 + j] ticket of the CTAs that serve peer j.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 15;
+constexpr int GATHER_CTRL_INTS = 64;   // [40 + j]: per-peer ticket
+struct GatherParams {
+    unsigned char *buf;
+    size_t pitch, row_bytes;
+    int row0, rows, my_slot, n_peers;
+    int *ctrl;
+    unsigned char *peer_buf[kMaxPeers];
+    int *peer_ctrl[kMaxPeers];
+    int peer_slot[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(HALO_THREADS) allgather_rows_kernel(const __grid_constant__ GatherParams p) {
+    const int j = blockIdx.x, part = blockIdx.y, nparts = gridDim.y;
+    __shared__ int ok;
+    const int e = p.ctrl[0];
+    if (e < 0) return;   // poisoned by an earlier timeout
+    int *pc = p.peer_ctrl[j];
+    const int ps = p.peer_slot[j];
+    if (threadIdx.x == 0) {
+        if (part == 0) st_release_sys(pc + 8 + p.my_slot, e);   // what peer j pushed into my copy last time is consumed
+        ok = spin_until(p.ctrl + 8 + ps, e) ? 1 : 0;            // and peer j has consumed what I pushed
+    }
+    __syncthreads();
+    if (ok) {
+        const size_t off = (size_t)p.row0 * p.pitch;
+        push_rows(p.peer_buf[j] + off, p.pitch, p.buf + off, p.pitch, p.row_bytes, p.rows, part, nparts);
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!ok) atomicExch(p.ctrl + 5, 1);
+        __threadfence();
+        // per-peer ticket: the last CTA of peer j publishes to it and waits for its rows
+        if (atomicAdd(reinterpret_cast<unsigned *>(p.ctrl + 40 + j), 1u) != (unsigned)nparts - 1) return;
+        p.ctrl[40 + j] = 0;
+        if (ok) {
+            st_release_sys(pc + 24 + p.my_slot, e + 1);
+            if (!spin_until(p.ctrl + 24 + ps, e + 1)) atomicExch(p.ctrl + 5, 1);
+        }
+        __threadfence();
+        // global ticket over the peers: every CTA of the launch has read `e` and finished
+        if (atomicAdd(reinterpret_cast<unsigned *>(p.ctrl + 1), 1u) == gridDim.x - 1) {
+            p.ctrl[1] = 0;
+            p.ctrl[0] = atomicAdd(p.ctrl + 5, 0) != 0 ? kPoisoned : e + 1;
+            __threadfence();
+        }
     }
 }
 
@@ -170,9 +261,9 @@ extern "C" int hb_ipc_close(void *peer_ptr) {
 
 extern "C" int hb_halo_ctrl_create(void **ctrl) {
     HB_REQUIRE(ctrl, HB_ERR_INVALID, "hb_halo_ctrl_create: null argument");
-    int rc = check_cuda(cudaMalloc(ctrl, CTRL_INTS * sizeof(int)), "cudaMalloc(halo control block)");
+    int rc = check_cuda(cudaMalloc(ctrl, GATHER_CTRL_INTS * sizeof(int)), "cudaMalloc(halo control block)");
     if (rc) return rc;
-    rc = check_cuda(cudaMemset(*ctrl, 0, CTRL_INTS * sizeof(int)), "cudaMemset(halo control block)");
+    rc = check_cuda(cudaMemset(*ctrl, 0, GATHER_CTRL_INTS * sizeof(int)), "cudaMemset(halo control block)");
     rc |= check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize()");
     return rc;
 }
@@ -189,6 +280,13 @@ extern "C" int hb_halo_status(const void *ctrl, int *exchanges, int *timed_out) 
     if (exchanges) *exchanges = h[0] < 0 ? -1 : h[0];   // -1: poisoned after a timeout
     if (timed_out) *timed_out = h[5];
     return rc;
+}
+
+// CTAs that share one push: one per 64 KiB, at most 32 (a 1-row halo stays a single CTA, the 5 MB level-0 halo of the
+// sharded pyramid and the 0.5 MB strips of an all-gather spread over enough SMs to fill NVLink)
+static int push_parts(size_t bytes) {
+    const size_t n = (bytes + 65535) / 65536;
+    return n < 1 ? 1 : n > 32 ? 32 : (int)n;
 }
 
 static int fill_halo_params(const hb_halo_desc *d, HaloParams &p) {
@@ -224,9 +322,35 @@ extern "C" int hb_halo_exchange_batch(const hb_halo_desc *const *descs, int n, v
     }
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_halo_exchange");
-    halo_exchange_kernel<<<n, 1024, 0, s>>>(b);
+    size_t bytes = 0;
+    for (int i = 0; i < n; ++i) bytes = bytes > (size_t)b.p[i].R * b.p[i].row_bytes ? bytes : (size_t)b.p[i].R * b.p[i].row_bytes;
+    halo_exchange_kernel<<<dim3(n, push_parts(bytes)), HALO_THREADS, 0, s>>>(b);
     g_launches++;
     return scope.finish();
 }
 
 extern "C" int hb_halo_exchange(const hb_halo_desc *d, void *stream) { return hb_halo_exchange_batch(&d, 1, stream); }
+
+extern "C" int hb_allgather_rows(const hb_gather_desc *d, void *stream) {
+    HB_REQUIRE(d && d->buf && d->ctrl, HB_ERR_INVALID, "hb_allgather_rows: null buffer / control block");
+    HB_REQUIRE(d->n_peers >= 1 && d->n_peers <= kMaxPeers && d->n_peers <= HB_MAX_PEERS, HB_ERR_INVALID, "hb_allgather_rows: 1..%d peers", kMaxPeers);
+    HB_REQUIRE(d->rows > 0 && d->row0 >= 0 && d->row_bytes > 0 && d->pitch_bytes >= d->row_bytes, HB_ERR_INVALID, "hb_allgather_rows: bad geometry");
+    HB_REQUIRE(d->my_slot >= 0 && d->my_slot < 16, HB_ERR_INVALID, "hb_allgather_rows: slot out of range");
+    GatherParams p;
+    memset(&p, 0, sizeof(p));
+    p.buf = static_cast<unsigned char *>(d->buf); p.pitch = d->pitch_bytes; p.row_bytes = d->row_bytes;
+    p.row0 = d->row0; p.rows = d->rows; p.my_slot = d->my_slot; p.n_peers = d->n_peers;
+    p.ctrl = static_cast<int *>(d->ctrl);
+    for (int j = 0; j < d->n_peers; ++j) {
+        HB_REQUIRE(d->peer_buf[j] && d->peer_ctrl[j] && d->peer_slot[j] >= 0 && d->peer_slot[j] < 16 && d->peer_slot[j] != d->my_slot, HB_ERR_INVALID,
+                   "hb_allgather_rows: peer %d incomplete", j);
+        p.peer_buf[j] = static_cast<unsigned char *>(d->peer_buf[j]);
+        p.peer_ctrl[j] = static_cast<int *>(d->peer_ctrl[j]);
+        p.peer_slot[j] = d->peer_slot[j];
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    OpScope scope(s, "hb_allgather_rows");
+    allgather_rows_kernel<<<dim3(d->n_peers, push_parts((size_t)d->rows * d->row_bytes)), HALO_THREADS, 0, s>>>(p);
+    g_launches++;
+    return scope.finish();
+}

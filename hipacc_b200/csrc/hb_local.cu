@@ -349,7 +349,8 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     // SUM-of-products fast variant: Domain holes ride along as zero coefficients.  That is exact for integer pixels
     // (0 * pixel adds nothing); for FLOAT pixels a hole over an inf / NaN pixel would poison the sum although the DSL
     // never visits that tap, so float images with holes take the domain-testing variant.
-    const bool fast = d->reduce_mode == HB_REDUCE_SUM && d->tap == HB_TAP_MUL && (visited == n || in.dtype != HB_F32);
+    const bool sum_of_products = d->reduce_mode == HB_REDUCE_SUM && d->tap == HB_TAP_MUL;
+    const bool fast = sum_of_products && (visited == n || in.dtype != HB_F32);
 
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_local_op");
@@ -362,7 +363,9 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
         if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, float, uchar>(p, fast, s);
         else if (it == HB_F32 && ot == HB_F32) {
             // hot path: persistent TMA-pipelined kernel (hb_local_tma.cu); anything it does not take runs staged
-            if (fast && d->epilogue == HB_EPI_CAST) rc = launch_local_tma_f32(p, visited == n, s);
+            // (the TMA kernel skips Domain holes itself: constexpr masks drop them, run-time masks are only taken when
+            // every tap is visited)
+            if (sum_of_products && d->epilogue == HB_EPI_CAST) rc = launch_local_tma_f32(p, visited == n, s);
             if (rc == HB_ERR_UNSUPPORTED) rc = launch_local<float, float, float>(p, fast, s);
         }
         else if (it == HB_S8 && ot == HB_S8) rc = launch_local<signed char, float, signed char>(p, fast, s);

@@ -342,3 +342,232 @@ def pyramid_traverse_strips(hb, pg, pl, mask, stream=None, group=None):
             pg.exchange(l + 1, stream, group)
             pl.exchange(l + 1, stream, group)
         pyramid_up_step(hb, pg, pl, l, stream)
+
+
+# ----------------------------------------------------------------------------- sharded pyramids, second design
+class P2PGather:
+    """All-gather of row strips over NVLink peer memory (hb_allgather_rows): every rank keeps the FULL image `buf`
+    (shape [height, stride], from hipacc_b200.alloc_image), owns rows [row0, row0 + rows) of it and pushes them into
+    every peer's copy with ONE kernel launch (one CTA per peer, device-side flags, CUDA-graph replayable)."""
+
+    def __init__(self, hb, buf, row0, rows, row_elems, world, rank, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.hb, self.L, self.desc, self.rank = hb, hb.lib(), None, rank
+        if world == 1:
+            return
+        assert world - 1 <= A.HB_MAX_PEERS
+        L = self.L
+        mem, cmem = A.hb_ipc_mem(), A.hb_ipc_mem()
+        self.ctrl = C.c_void_p()
+        es = buf.element_size()
+        err = None
+        try:
+            hb._check(L.hb_halo_ctrl_create(C.byref(self.ctrl)), "hb_halo_ctrl_create")
+            hb._check(L.hb_ipc_export(C.c_void_p(buf.data_ptr()), C.byref(mem)), "hb_ipc_export(buffer)")
+            hb._check(L.hb_ipc_export(self.ctrl, C.byref(cmem)), "hb_ipc_export(control block)")
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {rank}: {e}"
+        mine = {"mem": bytes(mem.handle), "ctrl": bytes(cmem.handle), "pitch": buf.stride(0) * es, "rows": buf.shape[0], "err": err}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        errs = [o["err"] for o in everyone if o["err"]]
+        if errs:
+            raise RuntimeError("P2PGather: CUDA IPC export failed: " + "; ".join(errs))
+        assert all(o["pitch"] == mine["pitch"] and o["rows"] == mine["rows"] for o in everyone), "P2PGather: the copies must share one layout"
+        d = A.hb_gather_desc()
+        d.buf, d.pitch_bytes, d.row_bytes = buf.data_ptr(), buf.stride(0) * es, row_elems * es
+        d.row0, d.rows, d.ctrl, d.my_slot, d.n_peers = row0, rows, self.ctrl, rank, world - 1
+        self._peers = []
+        try:
+            # peer order starts at my lower neighbour: the ranks do not all push to rank 0 first
+            for j, r in enumerate([(rank + 1 + k) % world for k in range(world - 1)]):
+                pm, pc = A.hb_ipc_mem(), A.hb_ipc_mem()
+                C.memmove(pm.handle, everyone[r]["mem"], 64)
+                C.memmove(pc.handle, everyone[r]["ctrl"], 64)
+                pb, pk = C.c_void_p(), C.c_void_p()
+                hb._check(L.hb_ipc_open(C.byref(pm), C.byref(pb)), "hb_ipc_open(buffer)")
+                hb._check(L.hb_ipc_open(C.byref(pc), C.byref(pk)), "hb_ipc_open(control block)")
+                self._peers.append((pb, pk))
+                d.peer_buf[j], d.peer_ctrl[j], d.peer_slot[j] = pb.value, pk.value, r
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {rank}: {e}"
+        status = [None] * world
+        dist.all_gather_object(status, err, group=group)
+        errs = [e for e in status if e]
+        if errs:
+            raise RuntimeError("P2PGather: mapping a peer's memory failed: " + "; ".join(errs))
+        self.desc = d
+
+    def gather(self, stream=None):
+        import ctypes as C
+        if self.desc is not None:
+            self.hb._check(self.L.hb_allgather_rows(C.byref(self.desc), self.hb.stream_ptr(stream)), "hb_allgather_rows")
+
+    def check(self):
+        import ctypes as C
+        if self.desc is None:
+            return
+        n, t = C.c_int(), C.c_int()
+        self.hb._check(self.L.hb_halo_status(self.ctrl, C.byref(n), C.byref(t)), "hb_halo_status")
+        if t.value or n.value < 0:
+            raise RuntimeError(f"rank {self.rank}: an all-gather timed out waiting for a peer")
+
+
+class PyramidShardPlan:
+    """Host logic of the sharded pyramid traversal with ONE halo exchange and ONE all-gather (SURVEY.md 8e "Pyramid").
+
+    Levels 0 .. G-1 are cut into row strips (every level at the same relative rows); levels >= G are small and every
+    rank keeps them in full.  Instead of exchanging halos before every level transition, a rank RECOMPUTES the few rows
+    of its neighbours it will need later ("extension" rows): the level-0 strip is loaded with E0 ghost rows per interior
+    side (one peer-to-peer exchange), every down step l-1 -> l then produces its strip of level l plus e[l] extension
+    rows per side from data it already holds, level G is all-gathered (each rank publishes its own rows), the coarse
+    levels are traversed redundantly on every rank, and the way up needs no communication at all: the up step towards
+    level l writes f[l] extension rows so that the next one finds its coarse ghost row locally.  Every pixel is computed
+    by the same kernels in the same order as in the unsharded traversal, so the results are bit-identical.
+
+    Ghost-row arithmetic (K = mask/2 + 2 rows is what the fused down kernel reads beyond its fine region):
+        f[0] = 0, f[l] = 2 (1 <= l < G)            fine-region extension of the up step that writes level l
+        e[G] = f[G-1] / 2                            lap(G-1) must cover the up step's fine region
+        e[l] = max(2 e[l+1] + K, f[l-1] / 2)         level l must hold what the next down step reads
+        V[l] = 2 e[l+1] + K                          valid rows needed beyond the strip at level l;  E0 = V[0]
+    """
+
+    def __init__(self, width, height, depth, world, rank, mask_size, gather_level=None, max_gather_pixels=1 << 20):
+        assert depth >= 1 and world >= 1 and 0 <= rank < world
+        assert height % (world << (depth - 1)) == 0 and width % (1 << (depth - 1)) == 0, \
+            "sharded pyramid: level-0 strips must be multiples of 2^(depth-1) rows and the width of 2^(depth-1)"
+        self.width, self.height, self.depth, self.world, self.rank, self.mask_size = width, height, depth, world, rank, mask_size
+        self.K = mask_size // 2 + 2
+        if gather_level is None:   # the finest level that is small enough to replicate
+            gather_level = next((l for l in range(1, depth) if (width >> l) * (height >> l) <= max_gather_pixels), depth - 1)
+        self.G = G = max(1, min(gather_level, depth - 1)) if depth > 1 else 1
+        self.top, self.bot = (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+        f = [0] + [2] * max(G - 1, 0)
+        e = [0] * (G + 2)
+        if depth > 1:
+            e[G] = f[G - 1] // 2
+            for l in range(G - 1, 0, -1):
+                e[l] = max(2 * e[l + 1] + self.K, f[l - 1] // 2)
+        self.f, self.e = f, e
+        self.V = [2 * e[l + 1] + self.K for l in range(G)] if depth > 1 else [0]
+        self.E0 = self.V[0] if world > 1 else 0
+        for l in range(min(G, depth)):
+            assert world == 1 or self.V[l] <= self.rows(l), \
+                f"level {l}: strips of {self.rows(l)} rows are thinner than the {self.V[l]} extension rows -- shard fewer ways or gather at a finer level"
+
+    # ---- geometry (global rows of level l)
+    def y0(self, l):
+        return (self.height >> l) * self.rank // self.world
+
+    def y1(self, l):
+        return (self.height >> l) * (self.rank + 1) // self.world
+
+    def rows(self, l):
+        return self.y1(l) - self.y0(l)
+
+    def sharded(self, l):
+        return l < self.G and self.world > 1
+
+    def buffer_span(self, l):
+        """global rows [a, b) level l's buffer holds on this rank"""
+        if not self.sharded(l):
+            return 0, self.height >> l
+        return self.y0(l) - self.V[l] * self.top, self.y1(l) + self.V[l] * self.bot
+
+    def span(self, l, ext):
+        """global rows of this rank's strip of level l extended by `ext` rows per interior side"""
+        if self.world == 1:
+            return 0, self.height >> l
+        return self.y0(l) - ext * self.top, self.y1(l) + ext * self.bot
+
+    def view_args(self, l, rows, ghost_wanted):
+        """(roi, ghost) in buffer coordinates for global rows `rows` = (r0, r1) of level l; ghosts are what the buffer
+        really holds beyond the region, capped at `ghost_wanted` (0 at the global image edge)"""
+        a, b = self.buffer_span(l)
+        r0, r1 = rows
+        assert a <= r0 < r1 <= b, (l, rows, (a, b))
+        gt, gb = min(r0 - a, ghost_wanted), min(b - r1, ghost_wanted)
+        return (self.width >> l, r1 - r0, 0, r0 - a), (gt, gb)
+
+
+class ShardedPyramid:
+    """This rank's buffers of a Gaussian and a Laplacian pyramid under a PyramidShardPlan, plus the traversal.
+    `transport` supplies the two communication steps: exchange0(stream) fills the E0 ghost rows of gaus(0),
+    gather(stream) publishes this rank's rows of gaus(G) into every rank's full copy.  With hb + torch.distributed
+    they are the peer-to-peer kernels (enable_p2p); tests emulate all ranks in one process with device copies."""
+
+    def __init__(self, plan, device, hb=None, stride_align=64):
+        import torch
+        self.plan, self.hb_mod = plan, hb
+        self.gaus, self.lap = [], []
+        for l in range(plan.depth):
+            a, b = plan.buffer_span(l)
+            w = plan.width >> l
+            stride = (w + stride_align - 1) // stride_align * stride_align
+            for dst in (self.gaus, self.lap):
+                if hb is None:
+                    dst.append(torch.zeros((b - a, stride), dtype=torch.float32, device=device))
+                else:   # whole CUDA allocations: exportable through CUDA IPC
+                    dst.append(hb.alloc_image(A.F32, stride, b - a, device=device, align_bytes=4 * stride_align).zero_())
+        self.halo0 = self.gatherG = None
+
+    def owned(self, pyr, l):
+        """this rank's rows of level l (levels >= G: its share of the replicated image)"""
+        p = self.plan
+        a, _ = p.buffer_span(l)
+        return pyr[l][p.y0(l) - a:p.y1(l) - a, :p.width >> l]
+
+    def strip0_plan(self):
+        p = self.plan
+        return StripPlan(p.width, p.height, p.world, p.rank, p.E0, A.CLAMP)
+
+    def enable_p2p(self, hb, group=None):
+        p = self.plan
+        if p.world == 1:
+            return
+        self.halo0 = P2PHalo(hb, self.gaus[0], self.strip0_plan(), group)
+        if p.G < p.depth:
+            self.gatherG = P2PGather(hb, self.gaus[p.G], p.y0(p.G), p.rows(p.G), p.width >> p.G, p.world, p.rank, group)
+
+    def _t(self, pyr, l, rows, ghost):
+        roi, g = self.plan.view_args(l, rows, ghost)
+        return (pyr[l][:, :self.plan.width >> l], roi, g)
+
+    def traverse(self, hb, mask, stream=None):
+        """Gaussian_Laplacian_Pyramid/src/main.cpp:199-248 on this rank's strips: 1 halo exchange + 1 all-gather."""
+        if self.halo0 is not None:
+            self.halo0.exchange(stream)
+        self.down_sharded(hb, mask, stream)
+        if self.gatherG is not None:
+            self.gatherG.gather(stream)
+        self.coarse_and_up(hb, mask, stream)
+
+    def down_sharded(self, hb, mask, stream=None):
+        """way down through the sharded levels (needs the E0 ghost rows of gaus(0)); ends with this rank's rows of
+        gaus(G) (+ e[G] extension rows) in its full copy of level G"""
+        p = self.plan
+        if p.world == 1:
+            return
+        for l in range(1, min(p.G, p.depth - 1) + 1):
+            c_rows = p.span(l, p.e[l])
+            f_rows = (2 * c_rows[0], 2 * c_rows[1])
+            hb.pyr_down(self._t(self.gaus, l - 1, f_rows, p.K), self._t(self.gaus, l, c_rows, 0), mask,
+                        lap_fine=self._t(self.lap, l - 1, f_rows, 0), stream=stream)
+
+    def coarse_and_up(self, hb, mask, stream=None):
+        """the replicated coarse levels (needs the gathered gaus(G)) and the whole way up: no communication"""
+        p = self.plan
+        first = 1 if p.world == 1 else p.G + 1
+        for l in range(first, p.depth):
+            w0, w1 = p.width >> (l - 1), p.width >> l
+            hb.pyr_down(self.gaus[l - 1][:, :w0], self.gaus[l][:, :w1], mask, lap_fine=self.lap[l - 1][:, :w0], stream=stream)
+        for l in range(p.depth - 2, -1, -1):
+            if l < p.G and p.world > 1:
+                f_rows = p.span(l, p.f[l])
+                c_rows = (f_rows[0] // 2, f_rows[1] // 2)
+                hb.pyr_up(self._t(self.gaus, l + 1, c_rows, 1), self._t(self.lap, l + 1, c_rows, 1),
+                          self._t(self.gaus, l, f_rows, 0), self._t(self.lap, l, f_rows, 0), stream=stream)
+            else:
+                w0, w1 = p.width >> l, p.width >> (l + 1)
+                hb.pyr_up(self.gaus[l + 1][:, :w1], self.lap[l + 1][:, :w1], self.gaus[l][:, :w0], self.lap[l][:, :w0], stream=stream)

@@ -364,6 +364,25 @@ int hb_halo_exchange(const hb_halo_desc *desc, void *stream);
  * Laplacian level before a pyramid up-transition */
 int hb_halo_exchange_batch(const hb_halo_desc *const *descs, int n, void *stream);
 
+/*
+ * All-gather of row strips over peer memory (coarse pyramid levels): every rank keeps the FULL image of a level,
+ * owns rows [row0, row0 + rows) of it and pushes them into the same rows of every peer's copy with one launch
+ * (one CTA per peer, device-side flags like hb_halo_exchange; CUDA-graph replayable).  All copies share the
+ * layout (pitch, height); `slot` = rank numbers used to index the flag arrays of the control blocks
+ * (hb_halo_ctrl_create).  With this the sharded pyramid needs no halo exchange below the gather level.
+ */
+#define HB_MAX_PEERS 15
+typedef struct {
+  void *buf;                 /* this rank's full copy */
+  size_t pitch_bytes, row_bytes;
+  int row0, rows;            /* the rows this rank owns and publishes */
+  void *ctrl;                /* this rank's control block */
+  int my_slot, n_peers;
+  void *peer_buf[HB_MAX_PEERS], *peer_ctrl[HB_MAX_PEERS];
+  int peer_slot[HB_MAX_PEERS];
+} hb_gather_desc;
+int hb_allgather_rows(const hb_gather_desc *desc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,19 @@ def test_new_struct_layouts_match_the_compiler(tmp_path):
     assert got == want
 
 
+def test_gather_desc_layout_matches_the_compiler(tmp_path):
+    import subprocess
+    src = tmp_path / "lay3.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hipacc_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %d\\n", sizeof(hb_gather_desc), offsetof(hb_gather_desc, ctrl),'
+                   'offsetof(hb_gather_desc, peer_ctrl), offsetof(hb_gather_desc, peer_slot), HB_MAX_PEERS);return 0;}\n')
+    exe = tmp_path / "lay3"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(A.hb_gather_desc), A.hb_gather_desc.ctrl.offset, A.hb_gather_desc.peer_ctrl.offset,
+                   A.hb_gather_desc.peer_slot.offset, A.HB_MAX_PEERS]
+
+
 def test_pyramid_sizes_truncate_like_the_reference():
     assert S.pyramid_sizes(16384, 16384, 8)[-1] == (128, 128)
     assert S.pyramid_sizes(101, 67, 3) == [(101, 67), (50, 33), (25, 16)]

@@ -886,3 +886,48 @@ def test_full_size_c5_pyramid_properties(hb, dev):
     err = (pg.levels[0] - img).abs().max().item()
     assert err <= 1e-5 * 1.0 + 1e-6   # (g - LF(c)) + LF(c) == g up to one float rounding
     assert torch.isfinite(pl.levels[0]).all().item()
+
+
+@pytest.mark.parametrize("world,h,w,depth,sz,G", [(2, 512, 392, 4, 5, 2), (4, 1024, 264, 4, 3, 2), (8, 4096, 256, 5, 5, 3), (3, 768, 520, 3, 7, 1), (2, 512, 128, 3, 5, 2)])
+def test_sharded_pyramid_one_exchange_one_gather_equals_unsharded(hb, dev, world, h, w, depth, sz, G):
+    """strips.ShardedPyramid (recompute-in-halo: ONE level-0 halo exchange + ONE all-gather of level G, no exchange
+    on the way up) gives bit-identical levels; all ranks emulated in one process, communication by device copies,
+    everything a rank does not own or compute is poisoned with NaN first."""
+    import torch
+    from hipacc_b200 import strips
+    img = to_dev(hb, synth.image_np("float32", w, h, seed=90 + world), dev)
+    pg = hb.Pyramid(img.clone(), depth)
+    pl = hb.Pyramid(torch.zeros_like(img), depth)
+    hb.pyramid_traverse(pg, pl, M.GAUSS[sz])
+
+    plans = [strips.PyramidShardPlan(w, h, depth, world, r, sz, gather_level=G) for r in range(world)]
+    sp = [strips.ShardedPyramid(p, dev) for p in plans]
+    for r, (p, s) in enumerate(zip(plans, sp)):
+        for l in range(depth):
+            s.gaus[l].fill_(float("nan"))
+            s.lap[l].fill_(float("nan"))
+        s.lap[depth - 1].zero_()          # the coarsest Laplacian level is never written (zeros, like the unsharded run)
+        s.owned(s.gaus, 0).copy_(img[p.y0(0):p.y1(0)])
+    # the one halo exchange: E0 rows of level 0 from each neighbour
+    for r, (p, s) in enumerate(zip(plans, sp)):
+        a, b = p.buffer_span(0)
+        s.gaus[0][:, :w].copy_(img[a:b])
+        assert p.E0 <= p.rows(0)
+    for s in sp:
+        s.down_sharded(hb, M.GAUSS[sz])
+    # the one all-gather: every rank publishes ITS rows of gaus(G)
+    Gl = plans[0].G
+    for r, (p, s) in enumerate(zip(plans, sp)):
+        for q, t in zip(plans, sp):
+            if t is not s:
+                t.gaus[Gl][p.y0(Gl):p.y1(Gl)].copy_(s.gaus[Gl][p.y0(Gl):p.y1(Gl)])
+    for s in sp:
+        s.coarse_and_up(hb, M.GAUSS[sz])
+    for l in range(depth):
+        got_g = torch.cat([s.owned(s.gaus, l) for s in sp])
+        got_l = torch.cat([s.owned(s.lap, l) for s in sp])
+        np.testing.assert_array_equal(to_np(got_g), to_np(pg.levels[l]))
+        np.testing.assert_array_equal(to_np(got_l), to_np(pl.levels[l]))
+        if l >= Gl:   # replicated levels: every rank holds the whole image
+            for s in sp:
+                np.testing.assert_array_equal(to_np(s.gaus[l][:, :w >> l]), to_np(pg.levels[l]))

@@ -107,3 +107,40 @@ def test_strip_pyramid_levels_align_across_ranks():
             assert all(tuple(p.bufs[l].shape)[0] == p.plans[l].buffer_rows for p in pyrs)
     with pytest.raises(AssertionError):
         strips.StripPyramid(256, 100, 3, 2, 0, 4, "cpu")   # 100 rows cannot be cut into 2 strips of multiples of 4
+
+
+def test_pyramid_shard_plan_geometry():
+    """PyramidShardPlan (one exchange + one all-gather): every region a level transition touches lies inside the rows
+    the rank holds, fine regions are twice their coarse regions and start on even global rows, and the fused down
+    kernel always finds its K ghost rows beyond the fine region on interior sides."""
+    for world, H, W, depth, sz in [(8, 16384, 16384, 8, 5), (2, 16384, 16384, 8, 5), (4, 1024, 264, 4, 3), (3, 768, 520, 3, 7), (1, 256, 256, 4, 5)]:
+        plans = [strips.PyramidShardPlan(W, H, depth, world, r, sz) for r in range(world)]
+        for p in plans:
+            assert 1 <= p.G <= max(depth - 1, 1)
+            if world == 1:
+                assert p.E0 == 0
+                continue
+            assert p.E0 == p.V[0] and p.E0 <= p.rows(0)
+            for l in range(1, p.G + 1):      # way down
+                c = p.span(l, p.e[l])
+                f = (2 * c[0], 2 * c[1])
+                roi, ghost = p.view_args(l - 1, f, p.K)
+                assert f[0] % 2 == 0 and roi[1] == 2 * (c[1] - c[0])
+                assert ghost[0] == (p.K if p.rank > 0 else 0) and ghost[1] == (p.K if p.rank < world - 1 else 0)
+                p.view_args(l, c, 0)         # asserts containment
+            for l in range(p.G - 1, -1, -1):  # way up
+                f = p.span(l, p.f[l])
+                c = (f[0] // 2, f[1] // 2)
+                assert f[0] % 2 == 0 and f[1] % 2 == 0
+                _, ghost = p.view_args(l + 1, c, 1)
+                assert ghost[0] == (1 if p.rank > 0 else 0) and ghost[1] == (1 if p.rank < world - 1 else 0)
+                # the Laplacian level written on the way down covers what the up step reads and rewrites
+                d = p.span(l + 1, p.e[l + 1])
+                assert 2 * d[0] <= f[0] and f[1] <= 2 * d[1]
+        # all ranks agree on G and the strips tile every level
+        assert len({p.G for p in plans}) == 1
+        for l in range(depth):
+            assert plans[0].y0(l) == 0 and plans[-1].y1(l) == H >> l
+            assert all(plans[i].y1(l) == plans[i + 1].y0(l) for i in range(world - 1))
+    with pytest.raises(AssertionError):
+        strips.PyramidShardPlan(256, 256, 6, 8, 1, 5, gather_level=5)   # 32-row strips cannot hold the extension rows
