@@ -49,6 +49,7 @@ def lib():
         L.hb_harris.argtypes = [C.POINTER(A.hb_harris_desc), C.c_void_p]
         L.hb_pyr_down.argtypes = [C.POINTER(A.hb_pyr_down_desc), C.c_void_p]
         L.hb_pyr_up.argtypes = [C.POINTER(A.hb_pyr_up_desc), C.c_void_p]
+        L.hb_pyr_traverse_coarse.argtypes = [C.POINTER(A.hb_pyr_coarse_desc), C.c_void_p]
         L.hb_image_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(A.hb_view)]
         L.hb_image_destroy.argtypes = [C.POINTER(A.hb_view)]
         L.hb_image_wrap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(A.hb_view)]
@@ -352,12 +353,59 @@ def pyr_up(coarse_gaus, coarse_lap, fine_gaus, fine_lap, stream=None):
     _check(lib().hb_pyr_up(C.byref(d), stream_ptr(stream)), "hb_pyr_up")
 
 
-def pyramid_traverse(pgaus, plap, mask, ptmp=None, stream=None):
+COARSE_PIXELS = 1 << 20   # levels of at most this many pixels form the "coarse end" (one cooperative launch)
+
+
+def pyr_traverse_coarse(gaus_levels, lap_levels, mask, stream=None):
+    """hb_pyr_traverse_coarse: way down and way up through a small pyramid (2..8 levels) in ONE launch.  Returns False
+    when the levels are not aligned exact halvings (the caller then walks them level by level)."""
+    import numpy as np
+    m = np.ascontiguousarray(mask, dtype=np.float32)
+    d = A.hb_pyr_coarse_desc()
+    d.levels = len(gaus_levels)
+    for i, (g, l) in enumerate(zip(gaus_levels, lap_levels)):
+        d.gaus[i], d.lap[i] = _v(g), _v(l)
+    d.size, d.coef_f32 = m.shape[0], m.ctypes.data_as(C.POINTER(C.c_float))
+    rc = lib().hb_pyr_traverse_coarse(C.byref(d), stream_ptr(stream))
+    if rc == A.HB_ERR_UNSUPPORTED:
+        return False
+    _check(rc, "hb_pyr_traverse_coarse")
+    return True
+
+
+def _halving(levels, l):
+    return levels[l - 1].shape[0] == 2 * levels[l].shape[0] and levels[l - 1].shape[1] == 2 * levels[l].shape[1]
+
+
+def coarse_start(levels, first=1):
+    """index c >= first of the finest level from which the rest of the pyramid is small enough for the one-launch
+    coarse traversal (exact halvings only, at least two levels), or None"""
+    depth = len(levels)
+    for c in range(first, depth - 1):
+        if levels[c].shape[0] * levels[c].shape[1] <= COARSE_PIXELS and depth - c <= 8 and all(_halving(levels, l) for l in range(c + 1, depth)):
+            return c
+    return None
+
+
+def pyramid_traverse(pgaus, plap, mask, ptmp=None, stream=None, fuse_coarse=False):
     """The traversal of Gaussian_Laplacian_Pyramid/src/main.cpp:199-248: way down builds the Gaussian and
-    Laplacian pyramids, way up restores / blends.  Host recursion only (dsl/pyramid.hpp:182-208)."""
+    Laplacian pyramids, way up restores / blends.  Host recursion only (dsl/pyramid.hpp:182-208).  fuse_coarse: run the coarse
+    end (levels of <= COARSE_PIXELS pixels) as one cooperative launch (hb_pyr_traverse_coarse).  Off by default: in a
+    CUDA-graph replay the six per-level kernels of the 1024^2 .. 128^2 tail take 43 us, the one-launch kernel 57 us
+    (tools/coarse_probe.py) -- every phase is a latency chain either way and a grid-wide barrier costs about what a
+    graph node does; it pays only for hosts that launch every kernel themselves."""
     depth = pgaus.depth
-    for l in range(1, depth):
+    c = coarse_start(pgaus.levels) if (fuse_coarse and ptmp is None) else None
+    last_down = depth - 1 if c is None else c
+    for l in range(1, last_down + 1):
         pyr_down(pgaus.levels[l - 1], pgaus.levels[l], mask, lap_fine=plap.levels[l - 1],
                  tmp=None if ptmp is None else ptmp.levels[l - 1], stream=stream)
-    for l in range(depth - 2, -1, -1):
+    first_up = depth - 2
+    if c is not None:
+        if pyr_traverse_coarse(pgaus.levels[c:], plap.levels[c:], mask, stream=stream):
+            first_up = c - 1
+        else:
+            for l in range(c + 1, depth):
+                pyr_down(pgaus.levels[l - 1], pgaus.levels[l], mask, lap_fine=plap.levels[l - 1], stream=stream)
+    for l in range(first_up, -1, -1):
         pyr_up(pgaus.levels[l + 1], plap.levels[l + 1], pgaus.levels[l], plap.levels[l], stream=stream)

@@ -101,6 +101,10 @@ class hb_pyr_up_desc(C.Structure):
     _fields_ = [("coarse_gaus", hb_view), ("coarse_lap", hb_view), ("fine_gaus", hb_view), ("fine_lap", hb_view)]
 
 
+class hb_pyr_coarse_desc(C.Structure):
+    _fields_ = [("levels", C.c_int), ("gaus", hb_view * 8), ("lap", hb_view * 8), ("size", C.c_int), ("coef_f32", C.POINTER(C.c_float))]
+
+
 class hb_ipc_mem(C.Structure):
     _fields_ = [("handle", C.c_ubyte * 64)]
 
@@ -155,6 +159,6 @@ EXPORTS = [
     "hb_local_op", "hb_bilateral", "hb_point_op",
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",
-    "hb_harris", "hb_pyr_down", "hb_pyr_up",
+    "hb_harris", "hb_pyr_down", "hb_pyr_up", "hb_pyr_traverse_coarse",
     "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange", "hb_halo_exchange_batch", "hb_allgather_rows",
 ]

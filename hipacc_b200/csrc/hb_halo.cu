@@ -54,25 +54,26 @@ __device__ __forceinline__ bool spin_until(int *flag, int want) {
 __device__ __forceinline__ void push_rows(unsigned char *dst, size_t dpitch, const unsigned char *src, size_t spitch, size_t row_bytes, int rows,
                                           int part, int nparts) {
     if ((row_bytes | dpitch | spitch | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0) {
+        // flattened 32-bit vector index (a 64-bit division per vector would cost more than the copy)
         constexpr int U = 8;
-        const size_t vpr = row_bytes / 16, total = vpr * rows;
-        const size_t step = (size_t)blockDim.x * U;
-        for (size_t base = (size_t)part * step; base < total; base += step * nparts) {
+        const unsigned vpr = (unsigned)(row_bytes / 16), total = vpr * (unsigned)rows;
+        const unsigned step = blockDim.x * U;
+        for (unsigned base = (unsigned)part * step; base < total; base += step * (unsigned)nparts) {
             uint4 v[U];
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const size_t i = base + (size_t)k * blockDim.x + threadIdx.x;
+                const unsigned i = base + k * blockDim.x + threadIdx.x;
                 if (i < total) {
-                    const size_t r = i / vpr, c = i - r * vpr;
-                    v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + r * spitch) + c);
+                    const unsigned r = i / vpr, c = i - r * vpr;
+                    v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)r * spitch) + c);
                 }
             }
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const size_t i = base + (size_t)k * blockDim.x + threadIdx.x;
+                const unsigned i = base + k * blockDim.x + threadIdx.x;
                 if (i < total) {
-                    const size_t r = i / vpr, c = i - r * vpr;
-                    reinterpret_cast<uint4 *>(dst + r * dpitch)[c] = v[k];
+                    const unsigned r = i / vpr, c = i - r * vpr;
+                    reinterpret_cast<uint4 *>(dst + (size_t)r * dpitch)[c] = v[k];
                 }
             }
         }

@@ -35,6 +35,7 @@ struct OpScope {
 bool stream_is_capturing(cudaStream_t s);
 // per-(device, stream) reduction scratch must exist before a capture starts (hb_reduce.cu)
 int reserve_reduce_scratch(cudaStream_t s);
+int reserve_pyramid_scratch(cudaStream_t s);   // grid-barrier words of hb_pyr_traverse_coarse (hb_pyramid.cu)
 
 inline hb_view norm_view(const hb_view &v) {
     hb_view o = v;

@@ -15,7 +15,10 @@
 #include "hb_common.cuh"
 #include "hb_internal.h"
 
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 namespace hb {
 
@@ -188,14 +191,24 @@ struct PyrFusedParams {
 // (the halo is recomputed by the neighbouring CTAs, 16 % extra FP work) from the staged fine tile: each thread
 // owns 2 coarse columns x 3 coarse rows and walks the S+4 fine rows once (row-stationary, 16-byte LDS).  Phase 2
 // is the DoG on 4x4 fine blocks from the two tiles.
-template <int S>
-__global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_constant__ PyrFusedParams p) {
+// COHERENT: the tile function runs inside the multi-level kernel below, where the fine level was written earlier in the
+// SAME launch by other CTAs -- its loads must then bypass the non-coherent read-only path (ld.global.cg instead of .nc)
+template <bool COHERENT> __device__ __forceinline__ float4 ld_f4(const float4 *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+template <bool COHERENT> __device__ __forceinline__ float2 ld_f2(const float2 *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+template <bool COHERENT> __device__ __forceinline__ float ld_f1(const float *p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+
+template <int S> struct DownSmem {
+    static constexpr int FROWS = 35 + 2 * (S / 2);     // row 0 <-> y = Y0 - 1 - H
+    static constexpr int FLOATS = FROWS * FD_FCOLS + FD_CROWS * FD_CCOLS;
+};
+
+// one 128 x 32 fine tile at tile coordinates (bx, by); every thread of the CTA must call it (it synchronises)
+template <int S, bool COHERENT>
+__device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int bx, const int by, float *ftile, float *ctile) {
     constexpr int H = S / 2;
-    constexpr int FROWS = 35 + 2 * H;                  // row 0 <-> y = Y0 - 1 - H
-    __shared__ __align__(16) float ftile[FROWS * FD_FCOLS];
-    __shared__ __align__(16) float ctile[FD_CROWS * FD_CCOLS];  // (0,0) <-> coarse (CX0-1, CY0-1)
+    constexpr int FROWS = DownSmem<S>::FROWS;
     const int tid = threadIdx.x;
-    const int X0 = blockIdx.x * FD_TW, Y0 = blockIdx.y * FD_TH;
+    const int X0 = bx * FD_TW, Y0 = by * FD_TH;
     const int CX0 = X0 >> 1, CY0 = Y0 >> 1;
 
     // ---- stage the fine tile, CLAMP applied here (Gaussian's BoundaryCondition), so phase 1 is branch-free.
@@ -213,7 +226,7 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
                 if (v < NV) {
                     const int r = v / VPR, c4 = v - r * VPR;
                     const int gy = min(max(ys + r, -p.fgt), p.fh - 1 + p.fgb);
-                    t[k] = __ldg(reinterpret_cast<const float4 *>(p.fine + (size_t)gy * p.fine_stride + xs) + c4);
+                    t[k] = ld_f4<COHERENT>(reinterpret_cast<const float4 *>(p.fine + (size_t)gy * p.fine_stride + xs) + c4);
                 }
             }
 #pragma unroll
@@ -229,12 +242,12 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
                 const float *row = p.fine + (size_t)gy * p.fine_stride;
                 float4 t;
                 if (gx >= 0 && gx + 3 < p.fw) {
-                    t = __ldg(reinterpret_cast<const float4 *>(row + gx));
+                    t = ld_f4<COHERENT>(reinterpret_cast<const float4 *>(row + gx));
                 } else {
-                    t.x = __ldg(row + min(max(gx, 0), p.fw - 1));
-                    t.y = __ldg(row + min(max(gx + 1, 0), p.fw - 1));
-                    t.z = __ldg(row + min(max(gx + 2, 0), p.fw - 1));
-                    t.w = __ldg(row + min(max(gx + 3, 0), p.fw - 1));
+                    t.x = ld_f1<COHERENT>(row + min(max(gx, 0), p.fw - 1));
+                    t.y = ld_f1<COHERENT>(row + min(max(gx + 1, 0), p.fw - 1));
+                    t.z = ld_f1<COHERENT>(row + min(max(gx + 2, 0), p.fw - 1));
+                    t.w = ld_f1<COHERENT>(row + min(max(gx + 3, 0), p.fw - 1));
                 }
                 reinterpret_cast<float4 *>(ftile)[v] = t;
             }
@@ -287,50 +300,57 @@ __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_cons
     // ---- phase 2: lap = fine - LF(coarse) on the thread's 4 x 4 fine block
     const int tx = tid & 31, ty = tid >> 5;
     const int x = X0 + 4 * tx, y = Y0 + 4 * ty;
-    if (x >= p.fw || y >= p.fh) return;
-    // interior strips (ghost rows present) have no vertical edge: their halo coarse rows -1 / ch were computed
-    // in phase 1 from the ghost rows
-    const bool edge = X0 == 0 || (Y0 == 0 && p.fgt == 0) || X0 + FD_TW >= p.fw || (Y0 + FD_TH >= p.fh && (p.fgb == 0 || Y0 + FD_TH > p.fh));
-    float o[4][4];
-    if (!edge) {
-        float c[4][4];
+    if (x < p.fw && y < p.fh) {
+        // interior strips (ghost rows present) have no vertical edge: their halo coarse rows -1 / ch were computed
+        // in phase 1 from the ghost rows
+        const bool edge = X0 == 0 || (Y0 == 0 && p.fgt == 0) || X0 + FD_TW >= p.fw || (Y0 + FD_TH >= p.fh && (p.fgb == 0 || Y0 + FD_TH > p.fh));
+        float o[4][4];
+        if (!edge) {
+            float c[4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 a = *reinterpret_cast<const float2 *>(ctile + (2 * ty + j) * FD_CCOLS + 2 * tx);
-            const float2 b = *reinterpret_cast<const float2 *>(ctile + (2 * ty + j) * FD_CCOLS + 2 * tx + 2);
-            c[j][0] = a.x; c[j][1] = a.y; c[j][2] = b.x; c[j][3] = b.y;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 f = *reinterpret_cast<const float4 *>(ftile + (4 * ty + j + 1 + H) * FD_FCOLS + 4 + 4 * tx);
-            o[j][0] = __fadd_rn(f.x, -lf_block(c, 0, j));
-            o[j][1] = __fadd_rn(f.y, -lf_block(c, 1, j));
-            o[j][2] = __fadd_rn(f.z, -lf_block(c, 2, j));
-            o[j][3] = __fadd_rn(f.w, -lf_block(c, 3, j));
-        }
-    } else {
-        auto at = [&](int cx, int cy) { return ctile[(cy - CY0 + 1) * FD_CCOLS + (cx - CX0 + 1)]; };
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
-                const float f = ftile[(yy - Y0 + 1 + H) * FD_FCOLS + 4 + (xx - X0)];
-                o[j][i] = __fadd_rn(f, -lf_half(at, xx, yy, p.cw, p.ch - 1 + (p.fgb > 0 ? 1 : 0), p.fgt == 0));
+            for (int j = 0; j < 4; ++j) {
+                const float2 a = *reinterpret_cast<const float2 *>(ctile + (2 * ty + j) * FD_CCOLS + 2 * tx);
+                const float2 b = *reinterpret_cast<const float2 *>(ctile + (2 * ty + j) * FD_CCOLS + 2 * tx + 2);
+                c[j][0] = a.x; c[j][1] = a.y; c[j][2] = b.x; c[j][3] = b.y;
             }
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (y + j >= p.fh) break;
-        float *dst = p.lap + (size_t)(y + j) * p.lap_stride + x;
-        if (x + 3 < p.fw) {
-            __stcs(reinterpret_cast<float4 *>(dst), make_float4(o[j][0], o[j][1], o[j][2], o[j][3]));
+            for (int j = 0; j < 4; ++j) {
+                const float4 f = *reinterpret_cast<const float4 *>(ftile + (4 * ty + j + 1 + H) * FD_FCOLS + 4 + 4 * tx);
+                o[j][0] = __fadd_rn(f.x, -lf_block(c, 0, j));
+                o[j][1] = __fadd_rn(f.y, -lf_block(c, 1, j));
+                o[j][2] = __fadd_rn(f.z, -lf_block(c, 2, j));
+                o[j][3] = __fadd_rn(f.w, -lf_block(c, 3, j));
+            }
         } else {
+            auto at = [&](int cx, int cy) { return ctile[(cy - CY0 + 1) * FD_CCOLS + (cx - CX0 + 1)]; };
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (x + i < p.fw) dst[i] = o[j][i];
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
+                    const float f = ftile[(yy - Y0 + 1 + H) * FD_FCOLS + 4 + (xx - X0)];
+                    o[j][i] = __fadd_rn(f, -lf_half(at, xx, yy, p.cw, p.ch - 1 + (p.fgb > 0 ? 1 : 0), p.fgt == 0));
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (y + j >= p.fh) break;
+            float *dst = p.lap + (size_t)(y + j) * p.lap_stride + x;
+            if (x + 3 < p.fw) {
+                __stcs(reinterpret_cast<float4 *>(dst), make_float4(o[j][0], o[j][1], o[j][2], o[j][3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x + i < p.fw) dst[i] = o[j][i];
+            }
         }
     }
+}
+
+template <int S>
+__global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_constant__ PyrFusedParams p) {
+    __shared__ __align__(16) float smem[DownSmem<S>::FLOATS];
+    pyr_down_tile<S, false>(p, blockIdx.x, blockIdx.y, smem, smem + DownSmem<S>::FROWS * FD_FCOLS);
 }
 
 struct PyrUpHalfParams {
@@ -344,9 +364,10 @@ struct PyrUpHalfParams {
 // Restore + Blend for the exact-halving case: 4 x 4 fine block per thread, the two 4 x 4 coarse neighbourhoods
 // come through the read-only path (each coarse value is used by ~16 fine pixels: L1/L2 hits), lap is read once
 // with 16-byte streaming loads, both outputs are written with 16-byte stores.
-__global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant__ PyrUpHalfParams p) {
+template <bool COHERENT>
+__device__ __forceinline__ void pyr_up_tile(const PyrUpHalfParams &p, const int bx, const int by) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int x = blockIdx.x * 128 + 4 * tx, y = blockIdx.y * 32 + 4 * ty;
+    const int x = bx * 128 + 4 * tx, y = by * 32 + 4 * ty;
     if (x >= p.fw || y >= p.fh) return;
     float l[4][4], og[4][4], ol[4][4];
     const bool full = x + 3 < p.fw && y + 3 < p.fh;
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) l[j][i] = p.fl[(size_t)min(y + j, p.fh - 1) * p.fl_stride + min(x + i, p.fw - 1)];
+            for (int i = 0; i < 4; ++i) l[j][i] = __ldcs(p.fl + (size_t)min(y + j, p.fh - 1) * p.fl_stride + min(x + i, p.fw - 1));
     }
     const int cy_max = p.ch - 1 + p.cgb;
     if (full && x > 0 && (y > 0 || p.cgt > 0)) {
@@ -373,14 +394,14 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
         for (int j = 0; j < 4; ++j) {
             const int cy = min(k - 1 + j, cy_max);   // >= cy_min: y == 0 takes this path only with ghost rows
             const float *rg = p.cg + (ptrdiff_t)cy * p.cg_stride, *rl = p.cl + (ptrdiff_t)cy * p.cl_stride;
-            g[j][0] = __ldg(rg + c0); c[j][0] = __ldg(rl + c0);
+            g[j][0] = ld_f1<COHERENT>(rg + c0); c[j][0] = ld_f1<COHERENT>(rl + c0);
             if (pair) {
-                const float2 a = __ldg(reinterpret_cast<const float2 *>(rg + m)), b = __ldg(reinterpret_cast<const float2 *>(rl + m));
+                const float2 a = ld_f2<COHERENT>(reinterpret_cast<const float2 *>(rg + m)), b = ld_f2<COHERENT>(reinterpret_cast<const float2 *>(rl + m));
                 g[j][1] = a.x; g[j][2] = a.y; c[j][1] = b.x; c[j][2] = b.y;
             } else {
-                g[j][1] = __ldg(rg + m); g[j][2] = __ldg(rg + c2); c[j][1] = __ldg(rl + m); c[j][2] = __ldg(rl + c2);
+                g[j][1] = ld_f1<COHERENT>(rg + m); g[j][2] = ld_f1<COHERENT>(rg + c2); c[j][1] = ld_f1<COHERENT>(rl + m); c[j][2] = ld_f1<COHERENT>(rl + c2);
             }
-            g[j][3] = __ldg(rg + c3); c[j][3] = __ldg(rl + c3);
+            g[j][3] = ld_f1<COHERENT>(rg + c3); c[j][3] = ld_f1<COHERENT>(rl + c3);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -390,8 +411,8 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
                 ol[j][i] = __fadd_rn(lf_block(c, i, j), __fdiv_rn(l[j][i], 2.0f));
             }
     } else {
-        auto atg = [&](int cx, int cy) { return __ldg(p.cg + (ptrdiff_t)cy * p.cg_stride + cx); };
-        auto atl = [&](int cx, int cy) { return __ldg(p.cl + (ptrdiff_t)cy * p.cl_stride + cx); };
+        auto atg = [&](int cx, int cy) { return ld_f1<COHERENT>(p.cg + (ptrdiff_t)cy * p.cg_stride + cx); };
+        auto atl = [&](int cx, int cy) { return ld_f1<COHERENT>(p.cl + (ptrdiff_t)cy * p.cl_stride + cx); };
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -412,6 +433,70 @@ __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 if (x + i < p.fw) { dg[i] = og[j][i]; dl[i] = ol[j][i]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant__ PyrUpHalfParams p) { pyr_up_tile<false>(p, blockIdx.x, blockIdx.y); }
+
+// ================================================================================================
+// The coarse end of a pyramid in ONE launch.  Below ~1024^2 every level transition is a few microseconds of work
+// behind a launch of its own (levels 4-7 of the 16384^2 pyramid: 6 launches, ~60 us of a 1.55 ms traversal, and the
+// part every rank repeats when the pyramid is sharded).  This cooperative kernel walks the whole tail -- way down
+// through all transitions, then way up -- with a grid-wide barrier between transitions: the same tile functions as
+// the per-level kernels (same arithmetic, same order: bit-identical), tiles handed out round-robin to the resident
+// CTAs, loads through the coherent path because a level written in one phase is read in the next.
+// ================================================================================================
+constexpr int kMaxCoarseTransitions = 7;
+struct PyrCoarseParams {
+    int n;                                   // transitions: levels 0 .. n of the small pyramid
+    PyrFusedParams down[kMaxCoarseTransitions];   // down[t]: level t -> t + 1
+    PyrUpHalfParams up[kMaxCoarseTransitions];    // up[t]  : level t + 1 -> t
+    unsigned *bar;                           // [0] arrivals (monotonic within the launch), [1] exit ticket
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &epoch) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++epoch;
+        __threadfence();                     // this CTA's stores are visible before it arrives
+        atomicAdd(bar, 1u);
+        const unsigned target = epoch * gridDim.x;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+template <int S>
+__global__ void __launch_bounds__(FD_NT) pyr_coarse_kernel(const __grid_constant__ PyrCoarseParams p) {
+    __shared__ __align__(16) float smem[DownSmem<S>::FLOATS];
+    float *ftile = smem, *ctile = smem + DownSmem<S>::FROWS * FD_FCOLS;
+    unsigned epoch = 0;
+    for (int t = 0; t < p.n; ++t) {          // way down
+        const PyrFusedParams &q = p.down[t];
+        const int ntx = (q.fw + FD_TW - 1) / FD_TW, nty = (q.fh + FD_TH - 1) / FD_TH;
+        for (int i = blockIdx.x; i < ntx * nty; i += gridDim.x) {
+            pyr_down_tile<S, true>(q, i % ntx, i / ntx, ftile, ctile);
+            __syncthreads();                 // the tiles are reused by the next iteration
+        }
+        grid_barrier(p.bar, epoch);
+    }
+    for (int t = p.n - 1; t >= 0; --t) {     // way up
+        const PyrUpHalfParams &q = p.up[t];
+        const int ntx = (q.fw + 127) / 128, nty = (q.fh + 31) / 32;
+        for (int i = blockIdx.x; i < ntx * nty; i += gridDim.x) pyr_up_tile<true>(q, i % ntx, i / ntx);
+        if (t > 0) grid_barrier(p.bar, epoch);
+    }
+    // the last CTA to leave resets the barrier for the next launch (every CTA has passed the last barrier by then)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(p.bar + 1, 1u) == gridDim.x - 1) {
+            p.bar[0] = 0;
+            p.bar[1] = 0;
+            __threadfence();
         }
     }
 }
@@ -528,6 +613,94 @@ extern "C" int hb_pyr_up(const hb_pyr_up_desc *d, void *stream) {
     OpScope scope(s, "hb_pyr_up");
     dim3 grid((fg.width + 31) / 32, (fg.height + 31) / 32);
     pyr_up_kernel<<<grid, dim3(32, 8), 0, s>>>(p);
+    g_launches++;
+    return scope.finish();
+}
+
+// ---- the coarse end of a pyramid in one cooperative launch -------------------------------------------------------
+namespace hb {
+static std::mutex g_bar_mutex;
+static std::map<std::pair<int, cudaStream_t>, unsigned *> g_bars;   // grid-barrier words, one pair per (device, stream)
+
+static int coarse_barrier(unsigned **out, cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_bar_mutex);
+    auto it = g_bars.find({dev, s});
+    if (it == g_bars.end()) {
+        HB_REQUIRE(!stream_is_capturing(s), HB_ERR_INVALID,
+                   "hb_pyr_traverse_coarse: the barrier words of this stream cannot be allocated inside a capture; begin it with hb_graph_begin");
+        unsigned *b = nullptr;
+        int rc = check_cuda(cudaMalloc(&b, 2 * sizeof(unsigned)), "cudaMalloc(grid barrier)");
+        if (!rc) rc = check_cuda(cudaMemset(b, 0, 2 * sizeof(unsigned)), "cudaMemset(grid barrier)");
+        if (rc) return rc;
+        it = g_bars.emplace(std::make_pair(dev, s), b).first;
+    }
+    *out = it->second;
+    return HB_OK;
+}
+int reserve_pyramid_scratch(cudaStream_t s) {
+    unsigned *b = nullptr;
+    return coarse_barrier(&b, s);
+}
+}  // namespace hb
+
+extern "C" int hb_pyr_traverse_coarse(const hb_pyr_coarse_desc *d, void *stream) {
+    HB_REQUIRE(d && d->coef_f32, HB_ERR_INVALID, "hb_pyr_traverse_coarse: null descriptor / mask");
+    HB_REQUIRE(d->levels >= 2 && d->levels <= kMaxCoarseTransitions + 1, HB_ERR_UNSUPPORTED, "hb_pyr_traverse_coarse: 2..%d levels", kMaxCoarseTransitions + 1);
+    HB_REQUIRE(d->size == 3 || d->size == 5 || d->size == 7, HB_ERR_UNSUPPORTED, "hb_pyr_traverse_coarse: mask size %d unsupported (3,5,7); no CPU fallback", d->size);
+    PyrCoarseParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = d->levels - 1;
+    PlaneRef g[kMaxCoarseTransitions + 1], l[kMaxCoarseTransitions + 1];
+    for (int i = 0; i < d->levels; ++i) {
+        const hb_view vg = norm_view(d->gaus[i]), vl = norm_view(d->lap[i]);
+        HB_REQUIRE(view_ok(vg) && view_ok(vl) && vg.dtype == HB_F32 && vl.dtype == HB_F32, HB_ERR_INVALID, "hb_pyr_traverse_coarse: level %d needs valid f32 views", i);
+        HB_REQUIRE(vg.ghost_top == 0 && vg.ghost_bottom == 0 && vl.ghost_top == 0 && vl.ghost_bottom == 0, HB_ERR_UNSUPPORTED,
+                   "hb_pyr_traverse_coarse: ghost rows are not supported (the coarse levels are replicated, not sharded)");
+        HB_REQUIRE(vg.width == vl.width && vg.height == vl.height, HB_ERR_INVALID, "hb_pyr_traverse_coarse: level %d gaus / lap sizes differ", i);
+        g[i] = plane_of(vg); l[i] = plane_of(vl);
+    }
+    for (int t = 0; t < p.n; ++t) {
+        const PlaneRef &f = g[t], &c = g[t + 1], &lf = l[t], &lc = l[t + 1];
+        // the fused tile functions need exact halving and 16-byte (fine) / 8-byte (coarse) aligned rows; anything else is the
+        // caller's per-level path (hb_pyr_down / hb_pyr_up)
+        HB_REQUIRE(f.w == 2 * c.w && f.h == 2 * c.h && vec_ok(f) && vec_ok(lf) && c.stride % 2 == 0 && lc.stride % 2 == 0 &&
+                       reinterpret_cast<uintptr_t>(region_base(c)) % 8 == 0 && reinterpret_cast<uintptr_t>(region_base(lc)) % 8 == 0,
+                   HB_ERR_UNSUPPORTED, "hb_pyr_traverse_coarse: transition %d is not an aligned exact halving; use hb_pyr_down / hb_pyr_up per level", t);
+        PyrFusedParams &q = p.down[t];
+        q.fine = region_base(f); q.coarse = region_base(c); q.lap = region_base(lf);
+        q.fine_stride = f.stride; q.coarse_stride = c.stride; q.lap_stride = lf.stride;
+        q.fw = f.w; q.fh = f.h; q.cw = c.w; q.ch = c.h;
+        for (int k = 0; k < d->size * d->size; ++k) q.coef[k] = d->coef_f32[k];
+        p.up[t] = PyrUpHalfParams{region_base(c), region_base(lc), region_base(f), region_base(lf), c.stride, lc.stride, f.stride, lf.stride, f.w, f.h, c.w, c.h, 0, 0};
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = coarse_barrier(&p.bar, s);
+    if (rc) return rc;
+    const void *kern = d->size == 3 ? (const void *)pyr_coarse_kernel<3> : d->size == 5 ? (const void *)pyr_coarse_kernel<5> : (const void *)pyr_coarse_kernel<7>;
+    // every CTA must be resident (grid-wide barrier): at most one CTA per SM, never more than the first level has tiles
+    const int tiles0 = ((p.down[0].fw + FD_TW - 1) / FD_TW) * ((p.down[0].fh + FD_TH - 1) / FD_TH);
+    static int per_sm = -1;   // resident CTAs per SM the grid may use (HB_COARSE_CTAS_PER_SM, tuning knob)
+    static int max_per_sm[3] = {0, 0, 0};
+    if (per_sm < 0) {
+        const char *e = getenv("HB_COARSE_CTAS_PER_SM");
+        per_sm = e ? atoi(e) : 2;
+        if (per_sm < 1) per_sm = 1;
+    }
+    const int ki = d->size == 3 ? 0 : d->size == 5 ? 1 : 2;
+    if (max_per_sm[ki] == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, FD_NT, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+        max_per_sm[ki] = nb;
+    }
+    const int cap = sm_count() * (per_sm < max_per_sm[ki] ? per_sm : max_per_sm[ki]);
+    int grid = cap < tiles0 ? cap : tiles0;
+    if (grid < 1) grid = 1;
+    OpScope scope(s, "hb_pyr_traverse_coarse");
+    void *args[] = {&p};
+    rc = check_cuda(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(FD_NT), args, 0, s), "cudaLaunchCooperativeKernel(pyr_coarse_kernel)");
+    if (rc) return rc;
     g_launches++;
     return scope.finish();
 }

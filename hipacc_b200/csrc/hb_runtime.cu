@@ -294,6 +294,7 @@ int hb_graph_begin(void *stream) {
     // allocations are illegal while capturing: the scratch a captured reduction bakes into the graph is reserved now
     // (one set per stream, never reallocated, so replays stay valid)
     int rc = reserve_reduce_scratch((cudaStream_t)stream);
+    if (!rc) rc = reserve_pyramid_scratch((cudaStream_t)stream);
     if (rc) return rc;
     return check_cuda(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture()");
 }

@@ -534,35 +534,85 @@ class ShardedPyramid:
         roi, g = self.plan.view_args(l, rows, ghost)
         return (pyr[l][:, :self.plan.width >> l], roi, g)
 
-    def traverse(self, hb, mask, stream=None):
-        """Gaussian_Laplacian_Pyramid/src/main.cpp:199-248 on this rank's strips: 1 halo exchange + 1 all-gather."""
-        if self.halo0 is not None:
+    def traverse(self, hb, mask, stream=None, overlap=True):
+        """Gaussian_Laplacian_Pyramid/src/main.cpp:199-248 on this rank's strips: 1 halo exchange + 1 all-gather.
+        overlap: the level-0 halo exchange runs on a side stream while the first down step works on the rows that
+        need no ghost rows; its two edge bands follow the join (fork / join events, capturable into a CUDA graph)."""
+        import torch
+        if self.halo0 is None:
+            self.down_sharded(hb, mask, stream)
+        elif not overlap or not self._can_split0():
             self.halo0.exchange(stream)
-        self.down_sharded(hb, mask, stream)
+            self.down_sharded(hb, mask, stream)
+        else:
+            st = torch.cuda.current_stream() if stream is None else stream
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.gaus[0].device)
+                self._ev = (torch.cuda.Event(), torch.cuda.Event())
+            self._ev[0].record(st)
+            self._side.wait_event(self._ev[0])
+            self.halo0.exchange(self._side)
+            self._ev[1].record(self._side)
+            self._down0(hb, mask, st, "interior")
+            st.wait_event(self._ev[1])
+            self._down0(hb, mask, st, "edges")
+            self.down_sharded(hb, mask, st, first=2)
         if self.gatherG is not None:
             self.gatherG.gather(stream)
         self.coarse_and_up(hb, mask, stream)
 
-    def down_sharded(self, hb, mask, stream=None):
+    _side = None
+    _ev = None
+    SPLIT_ROWS = 2   # coarse rows next to a strip edge whose fine footprint (+ K ghost rows) reaches into the ghost rows
+
+    def _can_split0(self):
+        p = self.plan
+        return p.world > 1 and p.depth > 1 and p.rows(1) > 4 * self.SPLIT_ROWS + 64
+
+    def _down_region(self, hb, mask, l, c_rows, stream):
+        p = self.plan
+        f_rows = (2 * c_rows[0], 2 * c_rows[1])
+        hb.pyr_down(self._t(self.gaus, l - 1, f_rows, p.K), self._t(self.gaus, l, c_rows, 0), mask,
+                    lap_fine=self._t(self.lap, l - 1, f_rows, 0), stream=stream)
+
+    def _down0(self, hb, mask, stream, which):
+        """the first down step (level 0 -> 1) in three row bands: the interior band reads only rows this rank owns"""
+        p = self.plan
+        full = p.span(1, p.e[1])
+        s = self.SPLIT_ROWS
+        lo = p.y0(1) + s if p.top else full[0]      # at the global image edge there is no ghost band
+        hi = p.y1(1) - s if p.bot else full[1]
+        if which == "interior":
+            self._down_region(hb, mask, 1, (lo, hi), stream)
+        else:
+            if p.top:
+                self._down_region(hb, mask, 1, (full[0], lo), stream)
+            if p.bot:
+                self._down_region(hb, mask, 1, (hi, full[1]), stream)
+
+    def down_sharded(self, hb, mask, stream=None, first=1):
         """way down through the sharded levels (needs the E0 ghost rows of gaus(0)); ends with this rank's rows of
         gaus(G) (+ e[G] extension rows) in its full copy of level G"""
         p = self.plan
         if p.world == 1:
             return
-        for l in range(1, min(p.G, p.depth - 1) + 1):
-            c_rows = p.span(l, p.e[l])
-            f_rows = (2 * c_rows[0], 2 * c_rows[1])
-            hb.pyr_down(self._t(self.gaus, l - 1, f_rows, p.K), self._t(self.gaus, l, c_rows, 0), mask,
-                        lap_fine=self._t(self.lap, l - 1, f_rows, 0), stream=stream)
+        for l in range(first, min(p.G, p.depth - 1) + 1):
+            self._down_region(hb, mask, l, p.span(l, p.e[l]), stream)
 
-    def coarse_and_up(self, hb, mask, stream=None):
+    def coarse_and_up(self, hb, mask, stream=None, fuse_coarse=False):
         """the replicated coarse levels (needs the gathered gaus(G)) and the whole way up: no communication"""
         p = self.plan
         first = 1 if p.world == 1 else p.G + 1
+        top_up = p.depth - 2
+        if p.world > 1 and p.depth - p.G >= 2 and fuse_coarse:
+            # the replicated levels G .. depth-1 in ONE cooperative launch (hb_pyr_traverse_coarse)
+            lv = lambda pyr: [pyr[l][:, :p.width >> l] for l in range(p.G, p.depth)]  # noqa: E731
+            if hb.pyr_traverse_coarse(lv(self.gaus), lv(self.lap), mask, stream=stream):
+                first, top_up = p.depth, p.G - 1
         for l in range(first, p.depth):
             w0, w1 = p.width >> (l - 1), p.width >> l
             hb.pyr_down(self.gaus[l - 1][:, :w0], self.gaus[l][:, :w1], mask, lap_fine=self.lap[l - 1][:, :w0], stream=stream)
-        for l in range(p.depth - 2, -1, -1):
+        for l in range(top_up, -1, -1):
             if l < p.G and p.world > 1:
                 f_rows = p.span(l, p.f[l])
                 c_rows = (f_rows[0] // 2, f_rows[1] // 2)

@@ -325,6 +325,24 @@ typedef struct {
 } hb_pyr_up_desc;
 int hb_pyr_up(const hb_pyr_up_desc *desc, void *stream);
 
+/*
+ * The COARSE END of a pyramid traversal in one launch: levels 0 .. levels-1 of a small pyramid (level 0 = its finest
+ * level, e.g. level 4 of the 16384^2 pyramid), equivalent to
+ *     for l = 1 .. levels-1 : hb_pyr_down(gaus[l-1] -> gaus[l], lap[l-1])        (fused form, no tmp)
+ *     for l = levels-2 .. 0 : hb_pyr_up(gaus[l+1], lap[l+1] -> gaus[l], lap[l])
+ * bit for bit, but as ONE cooperative kernel with grid-wide barriers between the transitions: below ~1024^2 a
+ * transition is a few microseconds of work behind a launch of its own.  Needs exact halving at every transition
+ * and 16-byte aligned rows (HB_ERR_UNSUPPORTED otherwise: use the per-level calls); lap[levels-1] is only read.
+ */
+#define HB_PYR_MAX_COARSE_LEVELS 8
+typedef struct {
+  int levels;
+  hb_view gaus[HB_PYR_MAX_COARSE_LEVELS], lap[HB_PYR_MAX_COARSE_LEVELS];
+  int size;               /* Gaussian mask size (3,5,7) */
+  const float *coef_f32;
+} hb_pyr_coarse_desc;
+int hb_pyr_traverse_coarse(const hb_pyr_coarse_desc *desc, void *stream);
+
 /* ------------------------------------------------------------------ peer-to-peer halo exchange */
 /*
  * Row-strip sharding across the GPUs of one box (BASELINE.json: halo rows exchanged peer to peer over

@@ -888,8 +888,9 @@ def test_full_size_c5_pyramid_properties(hb, dev):
     assert torch.isfinite(pl.levels[0]).all().item()
 
 
+@pytest.mark.parametrize("split", [False, True], ids=["one_launch_level0", "three_band_level0"])
 @pytest.mark.parametrize("world,h,w,depth,sz,G", [(2, 512, 392, 4, 5, 2), (4, 1024, 264, 4, 3, 2), (8, 4096, 256, 5, 5, 3), (3, 768, 520, 3, 7, 1), (2, 512, 128, 3, 5, 2)])
-def test_sharded_pyramid_one_exchange_one_gather_equals_unsharded(hb, dev, world, h, w, depth, sz, G):
+def test_sharded_pyramid_one_exchange_one_gather_equals_unsharded(hb, dev, world, h, w, depth, sz, G, split):
     """strips.ShardedPyramid (recompute-in-halo: ONE level-0 halo exchange + ONE all-gather of level G, no exchange
     on the way up) gives bit-identical levels; all ranks emulated in one process, communication by device copies,
     everything a rank does not own or compute is poisoned with NaN first."""
@@ -914,7 +915,13 @@ def test_sharded_pyramid_one_exchange_one_gather_equals_unsharded(hb, dev, world
         s.gaus[0][:, :w].copy_(img[a:b])
         assert p.E0 <= p.rows(0)
     for s in sp:
-        s.down_sharded(hb, M.GAUSS[sz])
+        if split:   # the form that overlaps the exchange: interior band (own rows only) first, edge bands after the halo arrived
+            assert s._can_split0()
+            s._down0(hb, M.GAUSS[sz], None, "interior")
+            s._down0(hb, M.GAUSS[sz], None, "edges")
+            s.down_sharded(hb, M.GAUSS[sz], first=2)
+        else:
+            s.down_sharded(hb, M.GAUSS[sz])
     # the one all-gather: every rank publishes ITS rows of gaus(G)
     Gl = plans[0].G
     for r, (p, s) in enumerate(zip(plans, sp)):
@@ -931,3 +938,65 @@ def test_sharded_pyramid_one_exchange_one_gather_equals_unsharded(hb, dev, world
         if l >= Gl:   # replicated levels: every rank holds the whole image
             for s in sp:
                 np.testing.assert_array_equal(to_np(s.gaus[l][:, :w >> l]), to_np(pg.levels[l]))
+
+
+@pytest.mark.parametrize("h,w,depth,sz", [(1024, 1024, 4, 5), (512, 768, 5, 3), (256, 640, 3, 7), (64, 128, 2, 5), (1024, 512, 8, 5)])
+def test_coarse_pyramid_in_one_launch_equals_per_level(hb, oracle, dev, h, w, depth, sz):
+    """hb_pyr_traverse_coarse (one cooperative kernel, grid-wide barriers between the transitions) is bit-identical
+    to the per-level kernels, also when replayed from a CUDA graph and on a second input (barrier words reset)."""
+    import torch
+    stream = torch.cuda.Stream(device=dev)
+    imgs = [synth.image_np("float32", w, h, seed=95 + k) for k in range(2)]
+    with torch.cuda.stream(stream):
+        pg = hb.Pyramid(to_dev(hb, imgs[0], dev), depth)
+        pl = hb.Pyramid(torch.zeros_like(pg.levels[0]), depth)
+        qg = hb.Pyramid(to_dev(hb, imgs[0], dev), depth)
+        ql = hb.Pyramid(torch.zeros_like(qg.levels[0]), depth)
+        for k in range(2):
+            for pyr, img in ((pg, imgs[k]), (qg, imgs[k])):
+                pyr.levels[0].copy_(torch.from_numpy(img).to(dev))
+            for l in range(depth):
+                pl.levels[l].zero_(); ql.levels[l].zero_()
+            hb.pyramid_traverse(pg, pl, M.GAUSS[sz], stream=stream, fuse_coarse=False)
+            assert hb.pyr_traverse_coarse(qg.levels, ql.levels, M.GAUSS[sz], stream=stream)
+            stream.synchronize()
+            for l in range(depth):
+                np.testing.assert_array_equal(to_np(qg.levels[l]), to_np(pg.levels[l]))
+                np.testing.assert_array_equal(to_np(ql.levels[l]), to_np(pl.levels[l]))
+        # graph replay
+        qg.levels[0].copy_(torch.from_numpy(imgs[0]).to(dev))
+        for l in range(depth):
+            ql.levels[l].zero_()
+        stream.synchronize()
+        with hb.Graph(stream) as g:
+            hb.pyr_traverse_coarse(qg.levels, ql.levels, M.GAUSS[sz], stream=stream)
+        g.launch()
+        stream.synchronize()
+        pg.levels[0].copy_(torch.from_numpy(imgs[0]).to(dev))
+        for l in range(depth):
+            pl.levels[l].zero_()
+        hb.pyramid_traverse(pg, pl, M.GAUSS[sz], stream=stream, fuse_coarse=False)
+        stream.synchronize()
+        for l in range(depth):
+            np.testing.assert_array_equal(to_np(qg.levels[l]), to_np(pg.levels[l]))
+        g.destroy()
+    if h * w <= 1 << 18:   # and against the oracle
+        og, ol = oracle.pyramid(imgs[0], depth, M.GAUSS[sz])
+        for l in range(depth):
+            np.testing.assert_array_equal(to_np(pg.levels[l]), og[l])
+
+
+def test_full_pyramid_with_fused_coarse_end_vs_oracle(hb, oracle, dev):
+    """pyramid_traverse(fuse_coarse=True) routes the levels of <= 2^20 pixels through the one-launch coarse traversal"""
+    import torch
+    img = synth.image_np("float32", 2048, 1024, seed=97)
+    og, ol = oracle.pyramid(img, 6, M.GAUSS5)
+    pg = hb.Pyramid(to_dev(hb, img, dev), 6)
+    pl = hb.Pyramid(torch.zeros_like(pg.levels[0]), 6)
+    assert hb.coarse_start(pg.levels) == 1
+    n0 = hb.launch_count()
+    hb.pyramid_traverse(pg, pl, M.GAUSS5, fuse_coarse=True)
+    assert hb.launch_count() - n0 == 3          # down 0->1, the coarse end, up 1->0
+    for lv in range(6):
+        np.testing.assert_array_equal(to_np(pg.levels[lv]), og[lv])
+        np.testing.assert_array_equal(to_np(pl.levels[lv]), ol[lv])
