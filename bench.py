@@ -640,21 +640,20 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
                  "note": f"strong scaling: ONE level-0 halo exchange ({plan.E0} rows per neighbour) + ONE all-gather of level {plan.G} "
                          f"({Wp >> plan.G}x{Hp >> plan.G}) per traversal, levels >= {plan.G} replicated, extension rows recomputed instead of exchanged; "
                          "single_gpu_ms = the unsharded traversal on this rank's GPU in the same run"}
-        if os.environ.get("HB_BENCH_PHASES") and p2p:   # diagnosis: device time of the traversal's phases (direct launches)
-            names = ["exchange0", "down_sharded", "gather", "coarse_and_up"]
-            acc = [0.0] * 4
-            for _ in range(6):
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-                dist.barrier()
-                ev[0].record(stream)
-                sp.halo0.exchange(stream); ev[1].record(stream)
-                sp.down_sharded(hb, M.GAUSS5, stream); ev[2].record(stream)
-                sp.gatherG.gather(stream); ev[3].record(stream)
-                sp.coarse_and_up(hb, M.GAUSS5, stream); ev[4].record(stream)
-                torch.cuda.synchronize()
-                for i in range(4):
-                    acc[i] += ev[i].elapsed_time(ev[i + 1]) / 6
-            sys.stderr.write(f"[rank {rank}] C5 phases (ms): " + ", ".join(f"{n_} {a_:.3f}" for n_, a_ in zip(names, acc)) + "\n")
+        if os.environ.get("HB_BENCH_PHASES") and p2p:   # diagnosis: GPU-timer marks between the kernels of the captured traversal
+            for mode in (False, True, "edges_on_side"):
+                marks = torch.zeros(16, dtype=torch.int64, device=dev)
+                gfn, _ = graphed(lambda: sp.traverse(hb, M.GAUSS5, stream=stream, marks=marks, overlap=mode))
+                acc = None
+                for _ in range(8):
+                    dist.barrier()
+                    gfn()
+                    torch.cuda.synchronize()
+                    m = marks.cpu().numpy()[:9].astype("float64")
+                    d_ = (m - m[0]) * 1e-3
+                    acc = d_ if acc is None else acc + d_
+                acc /= 8
+                sys.stderr.write(f"[rank {rank}] C5 timeline overlap={mode} (us after start): " + ", ".join(f"{n_}: {a_:.1f}" for n_, a_ in zip(strips.ShardedPyramid.MARK_NAMES[1:], acc[1:])) + "\n")
         if sp.halo0 is not None:
             sp.halo0.check()
         if sp.gatherG is not None:

@@ -49,6 +49,7 @@ def lib():
         L.hb_harris.argtypes = [C.POINTER(A.hb_harris_desc), C.c_void_p]
         L.hb_pyr_down.argtypes = [C.POINTER(A.hb_pyr_down_desc), C.c_void_p]
         L.hb_pyr_up.argtypes = [C.POINTER(A.hb_pyr_up_desc), C.c_void_p]
+        L.hb_pyr_dog.argtypes = [C.POINTER(A.hb_pyr_dog_desc), C.c_void_p]
         L.hb_pyr_traverse_coarse.argtypes = [C.POINTER(A.hb_pyr_coarse_desc), C.c_void_p]
         L.hb_image_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(A.hb_view)]
         L.hb_image_destroy.argtypes = [C.POINTER(A.hb_view)]
@@ -60,6 +61,7 @@ def lib():
         L.hb_image_copy.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_image_copy_region.argtypes = [C.POINTER(A.hb_view), C.POINTER(A.hb_view), C.c_void_p]
         L.hb_stream_synchronize.argtypes = [C.c_void_p]
+        L.hb_debug_timestamp.argtypes = [C.c_void_p, C.c_void_p]
         L.hb_stream_create.argtypes = [C.POINTER(C.c_void_p)]
         L.hb_stream_destroy.argtypes = [C.c_void_p]
         L.hb_graph_begin.argtypes = [C.c_void_p]
@@ -94,6 +96,11 @@ def set_timing(on):
 
 def last_kernel_ms():
     return float(lib().hb_last_kernel_ms())
+
+
+def timestamp(marks, index, stream=None):
+    """diagnostics: write the GPU nanosecond timer into marks[index] (a CUDA int64 tensor) in stream order"""
+    _check(lib().hb_debug_timestamp(C.c_void_p(marks.data_ptr() + 8 * index), stream_ptr(stream)), "hb_debug_timestamp")
 
 
 def launch_count():
@@ -345,6 +352,13 @@ def pyr_down(fine, coarse, mask, lap_fine=None, tmp=None, stream=None):
         d.lap_fine = _v(lap_fine)
     d.size, d.coef_f32 = m.shape[0], m.ctypes.data_as(C.POINTER(C.c_float))
     _check(lib().hb_pyr_down(C.byref(d), stream_ptr(stream)), "hb_pyr_down")
+
+
+def pyr_dog(fine, coarse, lap_fine, stream=None):
+    """lap_fine = fine - LF(coarse)  (hb_pyr_dog); operands as in pyr_down"""
+    d = A.hb_pyr_dog_desc()
+    d.fine, d.coarse, d.lap_fine = _v(fine), _v(coarse), _v(lap_fine)
+    _check(lib().hb_pyr_dog(C.byref(d), stream_ptr(stream)), "hb_pyr_dog")
 
 
 def pyr_up(coarse_gaus, coarse_lap, fine_gaus, fine_lap, stream=None):

@@ -97,6 +97,10 @@ class hb_pyr_down_desc(C.Structure):
     ]
 
 
+class hb_pyr_dog_desc(C.Structure):
+    _fields_ = [("fine", hb_view), ("coarse", hb_view), ("lap_fine", hb_view)]
+
+
 class hb_pyr_up_desc(C.Structure):
     _fields_ = [("coarse_gaus", hb_view), ("coarse_lap", hb_view), ("fine_gaus", hb_view), ("fine_lap", hb_view)]
 
@@ -155,10 +159,10 @@ EXPORTS = [
     "hb_init", "hb_device_count", "hb_sm_count", "hb_set_log_callback", "hb_last_error",
     "hb_image_create", "hb_image_destroy", "hb_image_wrap", "hb_image_write", "hb_image_read",
     "hb_image_copy", "hb_image_copy_region", "hb_image_write_region_async", "hb_image_read_region_async", "hb_set_timing", "hb_last_kernel_ms", "hb_launch_count",
-    "hb_stream_synchronize", "hb_stream_create", "hb_stream_destroy", "hb_graph_begin", "hb_graph_end", "hb_graph_launch", "hb_graph_destroy",
+    "hb_stream_synchronize", "hb_debug_timestamp", "hb_stream_create", "hb_stream_destroy", "hb_graph_begin", "hb_graph_end", "hb_graph_launch", "hb_graph_destroy",
     "hb_local_op", "hb_bilateral", "hb_point_op",
     "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",
-    "hb_harris", "hb_pyr_down", "hb_pyr_up", "hb_pyr_traverse_coarse",
+    "hb_harris", "hb_pyr_down", "hb_pyr_up", "hb_pyr_dog", "hb_pyr_traverse_coarse",
     "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange", "hb_halo_exchange_batch", "hb_allgather_rows",
 ]

@@ -203,7 +203,8 @@ template <int S> struct DownSmem {
 };
 
 // one 128 x 32 fine tile at tile coordinates (bx, by); every thread of the CTA must call it (it synchronises)
-template <int S, bool COHERENT>
+// DOG = false: blur + subsample only (lap is not written; the DifferenceOfGaussian runs as its own kernel, pyr_dog_half_kernel)
+template <int S, bool COHERENT, bool DOG = true>
 __device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int bx, const int by, float *ftile, float *ctile) {
     constexpr int H = S / 2;
     constexpr int FROWS = DownSmem<S>::FROWS;
@@ -295,6 +296,7 @@ __device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int
             }
         }
     }
+    if (!DOG) return;
     __syncthreads();
 
     // ---- phase 2: lap = fine - LF(coarse) on the thread's 4 x 4 fine block
@@ -347,10 +349,10 @@ __device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int
     }
 }
 
-template <int S>
+template <int S, bool DOG>
 __global__ void __launch_bounds__(FD_NT) pyr_down_fused_kernel(const __grid_constant__ PyrFusedParams p) {
     __shared__ __align__(16) float smem[DownSmem<S>::FLOATS];
-    pyr_down_tile<S, false>(p, blockIdx.x, blockIdx.y, smem, smem + DownSmem<S>::FROWS * FD_FCOLS);
+    pyr_down_tile<S, false, DOG>(p, blockIdx.x, blockIdx.y, smem, smem + DownSmem<S>::FROWS * FD_FCOLS);
 }
 
 struct PyrUpHalfParams {
@@ -439,6 +441,72 @@ __device__ __forceinline__ void pyr_up_tile(const PyrUpHalfParams &p, const int 
 
 __global__ void __launch_bounds__(256) pyr_up_half_kernel(const __grid_constant__ PyrUpHalfParams p) { pyr_up_tile<false>(p, blockIdx.x, blockIdx.y); }
 
+// DifferenceOfGaussian on its own for the exact-halving case: lap = fine - LF(coarse), 4 x 4 fine block per thread, the
+// coarse neighbourhood through the read-only path (ghost rows of the coarse plane like pyr_up_half_kernel).  Same
+// arithmetic as phase 2 of the fused down kernel.  PyrUpHalfParams: cg = coarse, fg = fine (read), fl = lap (written).
+__global__ void __launch_bounds__(256) pyr_dog_half_kernel(const __grid_constant__ PyrUpHalfParams p) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * 128 + 4 * tx, y = blockIdx.y * 32 + 4 * ty;
+    if (x >= p.fw || y >= p.fh) return;
+    float f[4][4], o[4][4];
+    const bool full = x + 3 < p.fw && y + 3 < p.fh;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (full) {
+            const float4 t = __ldcs(reinterpret_cast<const float4 *>(p.fg + (size_t)(y + j) * p.fg_stride + x));
+            f[j][0] = t.x; f[j][1] = t.y; f[j][2] = t.z; f[j][3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[j][i] = __ldg(p.fg + (size_t)min(y + j, p.fh - 1) * p.fg_stride + min(x + i, p.fw - 1));
+        }
+    }
+    const int cy_max = p.ch - 1 + p.cgb;
+    if (full && x > 0 && (y > 0 || p.cgt > 0)) {
+        const int m = x >> 1, k = y >> 1;
+        float g[4][4];
+        const int c0 = m - 1, c3 = min(m + 2, p.cw - 1), c2 = min(m + 1, p.cw - 1);
+        const bool pair = (p.cg_stride % 2 == 0) && m + 1 < p.cw && (reinterpret_cast<uintptr_t>(p.cg) % 8 == 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cy = min(k - 1 + j, cy_max);
+            const float *rg = p.cg + (ptrdiff_t)cy * p.cg_stride;
+            g[j][0] = __ldg(rg + c0);
+            if (pair) {
+                const float2 a = __ldg(reinterpret_cast<const float2 *>(rg + m));
+                g[j][1] = a.x; g[j][2] = a.y;
+            } else {
+                g[j][1] = __ldg(rg + m); g[j][2] = __ldg(rg + c2);
+            }
+            g[j][3] = __ldg(rg + c3);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[j][i] = __fadd_rn(f[j][i], -lf_block(g, i, j));
+    } else {
+        auto atg = [&](int cx, int cy) { return __ldg(p.cg + (ptrdiff_t)cy * p.cg_stride + cx); };
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xx = min(x + i, p.fw - 1), yy = min(y + j, p.fh - 1);
+                o[j][i] = __fadd_rn(f[j][i], -lf_half(atg, xx, yy, p.cw, cy_max, p.cgt == 0));
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (y + j >= p.fh) break;
+        float *dl = p.fl + (size_t)(y + j) * p.fl_stride + x;
+        if (x + 3 < p.fw) {
+            __stcs(reinterpret_cast<float4 *>(dl), make_float4(o[j][0], o[j][1], o[j][2], o[j][3]));
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < p.fw) dl[i] = o[j][i];
+        }
+    }
+}
+
 // ================================================================================================
 // The coarse end of a pyramid in ONE launch.  Below ~1024^2 every level transition is a few microseconds of work
 // behind a launch of its own (levels 4-7 of the 16384^2 pyramid: 6 launches, ~60 us of a 1.55 ms traversal, and the
@@ -516,16 +584,17 @@ extern "C" int hb_pyr_down(const hb_pyr_down_desc *d, void *stream) {
     HB_REQUIRE(d->size == 3 || d->size == 5 || d->size == 7, HB_ERR_UNSUPPORTED, "hb_pyr_down: mask size %d unsupported (3,5,7); no CPU fallback", d->size);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = HB_OK;
-    if (!d->tmp.data && d->lap_fine.data && fine.width == 2 * coarse.width && fine.height == 2 * coarse.height) {
-        // exact-halving transition: blur + subsample + DoG in one kernel
-        hb_view lap = norm_view(d->lap_fine);
-        HB_REQUIRE(view_ok(lap) && lap.dtype == HB_F32 && lap.width == fine.width && lap.height == fine.height, HB_ERR_INVALID,
+    if (!d->tmp.data && fine.width == 2 * coarse.width && fine.height == 2 * coarse.height) {
+        // exact-halving transition: blur + subsample (+ DoG when lap_fine is given) in one kernel
+        const bool dog = d->lap_fine.data != nullptr;
+        hb_view lap = dog ? norm_view(d->lap_fine) : fine;
+        HB_REQUIRE(!dog || (view_ok(lap) && lap.dtype == HB_F32 && lap.width == fine.width && lap.height == fine.height), HB_ERR_INVALID,
                    "hb_pyr_down: lap_fine must be an f32 view of the fine level's size");
         const PlaneRef f = plane_of(fine), c = plane_of(coarse), l = plane_of(lap);
         if (vec_ok(f) && vec_ok(l) && c.stride % 2 == 0 && reinterpret_cast<uintptr_t>(region_base(c)) % 8 == 0) {
             PyrFusedParams p;
             memset(&p, 0, sizeof(p));
-            p.fine = region_base(f); p.coarse = region_base(c); p.lap = region_base(l);
+            p.fine = region_base(f); p.coarse = region_base(c); p.lap = dog ? region_base(l) : nullptr;
             p.fine_stride = f.stride; p.coarse_stride = c.stride; p.lap_stride = l.stride;
             p.fw = f.w; p.fh = f.h; p.cw = c.w; p.ch = c.h;
             // ghost rows (row-strip sharding): the coarse halo row above needs fine rows down to -(H+1), the one
@@ -534,11 +603,17 @@ extern "C" int hb_pyr_down(const hb_pyr_down_desc *d, void *stream) {
             HB_REQUIRE((p.fgt == 0 || p.fgt >= d->size / 2 + 1) && (p.fgb == 0 || p.fgb >= d->size / 2 + 2), HB_ERR_INVALID,
                        "hb_pyr_down: a sharded fine level needs >= %d ghost rows above and >= %d below", d->size / 2 + 1, d->size / 2 + 2);
             for (int k = 0; k < d->size * d->size; ++k) p.coef[k] = d->coef_f32[k];
-            OpScope scope(s, "hb_pyr_down(fused blur+subsample+DoG)");
+            OpScope scope(s, dog ? "hb_pyr_down(fused blur+subsample+DoG)" : "hb_pyr_down(fused blur+subsample)");
             dim3 grid((p.fw + FD_TW - 1) / FD_TW, (p.fh + FD_TH - 1) / FD_TH);
-            if (d->size == 3) pyr_down_fused_kernel<3><<<grid, FD_NT, 0, s>>>(p);
-            else if (d->size == 5) pyr_down_fused_kernel<5><<<grid, FD_NT, 0, s>>>(p);
-            else pyr_down_fused_kernel<7><<<grid, FD_NT, 0, s>>>(p);
+            if (dog) {
+                if (d->size == 3) pyr_down_fused_kernel<3, true><<<grid, FD_NT, 0, s>>>(p);
+                else if (d->size == 5) pyr_down_fused_kernel<5, true><<<grid, FD_NT, 0, s>>>(p);
+                else pyr_down_fused_kernel<7, true><<<grid, FD_NT, 0, s>>>(p);
+            } else {
+                if (d->size == 3) pyr_down_fused_kernel<3, false><<<grid, FD_NT, 0, s>>>(p);
+                else if (d->size == 5) pyr_down_fused_kernel<5, false><<<grid, FD_NT, 0, s>>>(p);
+                else pyr_down_fused_kernel<7, false><<<grid, FD_NT, 0, s>>>(p);
+            }
             g_launches++;
             return scope.finish();
         }
@@ -613,6 +688,34 @@ extern "C" int hb_pyr_up(const hb_pyr_up_desc *d, void *stream) {
     OpScope scope(s, "hb_pyr_up");
     dim3 grid((fg.width + 31) / 32, (fg.height + 31) / 32);
     pyr_up_kernel<<<grid, dim3(32, 8), 0, s>>>(p);
+    g_launches++;
+    return scope.finish();
+}
+
+// DifferenceOfGaussian of the pyramid sample on its own: lap_fine = fine - LF(coarse)
+extern "C" int hb_pyr_dog(const hb_pyr_dog_desc *d, void *stream) {
+    HB_REQUIRE(d, HB_ERR_INVALID, "hb_pyr_dog: null descriptor");
+    hb_view fine = norm_view(d->fine), coarse = norm_view(d->coarse), lap = norm_view(d->lap_fine);
+    HB_REQUIRE(view_ok(fine) && view_ok(coarse) && view_ok(lap), HB_ERR_INVALID, "hb_pyr_dog: malformed view");
+    HB_REQUIRE(fine.dtype == HB_F32 && coarse.dtype == HB_F32 && lap.dtype == HB_F32, HB_ERR_UNSUPPORTED, "hb_pyr_dog: f32 only; no CPU fallback");
+    HB_REQUIRE(lap.width == fine.width && lap.height == fine.height, HB_ERR_INVALID, "hb_pyr_dog: lap_fine must have the fine level's size");
+    cudaStream_t s = (cudaStream_t)stream;
+    const PlaneRef f = plane_of(fine), c = plane_of(coarse), l = plane_of(lap);
+    if (f.w == 2 * c.w && f.h == 2 * c.h && vec_ok(f) && vec_ok(l)) {
+        PyrUpHalfParams q{region_base(c), region_base(c), region_base(f), region_base(l), c.stride, c.stride, f.stride, l.stride, f.w, f.h, c.w, c.h,
+                          coarse.ghost_top, coarse.ghost_bottom};
+        OpScope scope(s, "hb_pyr_dog(exact halving)");
+        dim3 grid((f.w + 127) / 128, (f.h + 31) / 32);
+        pyr_dog_half_kernel<<<grid, 256, 0, s>>>(q);
+        g_launches++;
+        return scope.finish();
+    }
+    HB_REQUIRE(coarse.ghost_top == 0 && coarse.ghost_bottom == 0, HB_ERR_UNSUPPORTED,
+               "hb_pyr_dog: ghost rows (row-strip sharding) need the exact-halving path (even level sizes, 16-byte aligned rows)");
+    PyrDogParams p{plane_of(fine), plane_of(coarse), plane_of(lap)};
+    OpScope scope(s, "hb_pyr_dog");
+    dim3 grid((lap.width + 31) / 32, (lap.height + 31) / 32);
+    pyr_dog_kernel<<<grid, dim3(32, 8), 0, s>>>(p);
     g_launches++;
     return scope.finish();
 }

@@ -169,11 +169,23 @@ bool make_tile_map(CUtensorMap *out, const void *base, int dtype, int img_w, int
     return true;
 }
 
+__global__ void timestamp_kernel(unsigned long long *slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+
 }  // namespace hb
 
 using namespace hb;
 
 extern "C" {
+
+int hb_debug_timestamp(void *slot_device, void *stream) {
+    HB_REQUIRE(slot_device, HB_ERR_INVALID, "hb_debug_timestamp: null slot");
+    timestamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<unsigned long long *>(slot_device));
+    return check_cuda(cudaGetLastError(), "hb_debug_timestamp");
+}
 
 int hb_device_count(void) {
     int n = 0;

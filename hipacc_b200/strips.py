@@ -428,13 +428,19 @@ class PyramidShardPlan:
 
     Ghost-row arithmetic (K = mask/2 + 2 rows is what the fused down kernel reads beyond its fine region):
         f[0] = 0, f[l] = 2 (1 <= l < G)            fine-region extension of the up step that writes level l
-        e[G] = f[G-1] / 2                            lap(G-1) must cover the up step's fine region
-        e[l] = max(2 e[l+1] + K, f[l-1] / 2)         level l must hold what the next down step reads
+        e[G] = f[G-1] / 2 + d                        lap(G-1) must cover the up step's fine region
+        e[l] = max(2 e[l+1] + K, f[l-1] / 2 + d)     level l must hold what the next down step reads
+                                                     (d = 1 with split_dog: the separate DoG kernel reads one more coarse row)
         V[l] = 2 e[l+1] + K                          valid rows needed beyond the strip at level l;  E0 = V[0]
     """
 
-    def __init__(self, width, height, depth, world, rank, mask_size, gather_level=None, max_gather_pixels=1 << 20):
+    def __init__(self, width, height, depth, world, rank, mask_size, gather_level=None, max_gather_pixels=1 << 20, split_dog=False):
         assert depth >= 1 and world >= 1 and 0 <= rank < world
+        # split_dog: the DifferenceOfGaussian of every sharded level runs as its own kernel (hb_pyr_dog) on a second
+        # stream, in the shadow of the latency-bound chain blur+subsample -> ... -> all-gather -> coarse levels.  The
+        # separate DoG reads one coarse row beyond its region, so every extension is one row larger (d = 1).
+        self.split_dog = bool(split_dog)
+        d_ = 1 if split_dog else 0
         assert height % (world << (depth - 1)) == 0 and width % (1 << (depth - 1)) == 0, \
             "sharded pyramid: level-0 strips must be multiples of 2^(depth-1) rows and the width of 2^(depth-1)"
         self.width, self.height, self.depth, self.world, self.rank, self.mask_size = width, height, depth, world, rank, mask_size
@@ -446,9 +452,9 @@ class PyramidShardPlan:
         f = [0] + [2] * max(G - 1, 0)
         e = [0] * (G + 2)
         if depth > 1:
-            e[G] = f[G - 1] // 2
+            e[G] = f[G - 1] // 2 + d_
             for l in range(G - 1, 0, -1):
-                e[l] = max(2 * e[l + 1] + self.K, f[l - 1] // 2)
+                e[l] = max(2 * e[l + 1] + self.K, f[l - 1] // 2 + d_)
         self.f, self.e = f, e
         self.V = [2 * e[l + 1] + self.K for l in range(G)] if depth > 1 else [0]
         self.E0 = self.V[0] if world > 1 else 0
@@ -534,32 +540,68 @@ class ShardedPyramid:
         roi, g = self.plan.view_args(l, rows, ghost)
         return (pyr[l][:, :self.plan.width >> l], roi, g)
 
-    def traverse(self, hb, mask, stream=None, overlap=True):
+    def traverse(self, hb, mask, stream=None, overlap=True, marks=None):
         """Gaussian_Laplacian_Pyramid/src/main.cpp:199-248 on this rank's strips: 1 halo exchange + 1 all-gather.
         overlap: the level-0 halo exchange runs on a side stream while the first down step works on the rows that
         need no ghost rows; its two edge bands follow the join (fork / join events, capturable into a CUDA graph)."""
         import torch
+        mark = (lambda i, s_: hb.timestamp(marks, i, s_)) if marks is not None else (lambda i, s_: None)
+        p = self.plan
+        st = torch.cuda.current_stream() if stream is None else stream
+        mark(0, st)
+        split = p.split_dog and self.halo0 is not None
         if self.halo0 is None:
-            self.down_sharded(hb, mask, stream)
+            self.down_sharded(hb, mask, st)
         elif not overlap or not self._can_split0():
-            self.halo0.exchange(stream)
-            self.down_sharded(hb, mask, stream)
+            self.halo0.exchange(st)
+            mark(1, st)
+            self._down_region(hb, mask, 1, p.span(1, p.e[1]), st, dog=not split)
+            mark(2, st); mark(3, st)
         else:
-            st = torch.cuda.current_stream() if stream is None else stream
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.gaus[0].device)
                 self._ev = (torch.cuda.Event(), torch.cuda.Event())
             self._ev[0].record(st)
             self._side.wait_event(self._ev[0])
             self.halo0.exchange(self._side)
+            mark(1, self._side)
+            # the two edge bands follow the exchange on the side stream and overlap the tail of the interior band
+            self._down0(hb, mask, self._side, "edges", dog=not split)
+            mark(3, self._side)
             self._ev[1].record(self._side)
-            self._down0(hb, mask, st, "interior")
+            self._down0(hb, mask, st, "interior", dog=not split)
+            mark(2, st)
             st.wait_event(self._ev[1])
-            self._down0(hb, mask, st, "edges")
-            self.down_sharded(hb, mask, st, first=2)
+        if self.halo0 is not None:
+            if split:
+                # critical chain on `st`: blur+subsample only.  The DoG of level l-1 needs gaus(l) (just produced) and runs
+                # on the DoG stream; the up step that consumes lap(l-1) waits for it (coarse_and_up).
+                if self._dog_stream is None:
+                    self._dog_stream = torch.cuda.Stream(device=self.gaus[0].device)
+                    self._dog_ev = [torch.cuda.Event() for _ in range(2 * p.depth)]
+                for l in range(1, min(p.G, p.depth - 1) + 1):
+                    if l > 1:
+                        self._down_region(hb, mask, l, p.span(l, p.e[l]), st, dog=False)
+                    self._dog_ev[l].record(st)
+                    self._dog_stream.wait_event(self._dog_ev[l])
+                    c_rows = p.span(l, p.e[l] - 1)
+                    f_rows = (2 * c_rows[0], 2 * c_rows[1])
+                    hb.pyr_dog(self._t(self.gaus, l - 1, f_rows, 0), self._t(self.gaus, l, c_rows, 1), self._t(self.lap, l - 1, f_rows, 0), stream=self._dog_stream)
+                    self._dog_ev[p.depth + l].record(self._dog_stream)
+            else:
+                self.down_sharded(hb, mask, st, first=2)
+        mark(4, st)
         if self.gatherG is not None:
-            self.gatherG.gather(stream)
-        self.coarse_and_up(hb, mask, stream)
+            self.gatherG.gather(st)
+        mark(5, st)
+        self.coarse_and_up(hb, mask, st, marks=marks, wait_dog=split)
+        mark(8, st)
+
+    _dog_stream = None
+    _dog_ev = None
+
+    MARK_NAMES = ["start", "exchange0 done", "down L0 interior done", "down L0 edges done", "down L1..G done", "gather done",
+                  "replicated levels done", "up to level 1 done", "end"]
 
     _side = None
     _ev = None
@@ -569,13 +611,13 @@ class ShardedPyramid:
         p = self.plan
         return p.world > 1 and p.depth > 1 and p.rows(1) > 4 * self.SPLIT_ROWS + 64
 
-    def _down_region(self, hb, mask, l, c_rows, stream):
+    def _down_region(self, hb, mask, l, c_rows, stream, dog=True):
         p = self.plan
         f_rows = (2 * c_rows[0], 2 * c_rows[1])
         hb.pyr_down(self._t(self.gaus, l - 1, f_rows, p.K), self._t(self.gaus, l, c_rows, 0), mask,
-                    lap_fine=self._t(self.lap, l - 1, f_rows, 0), stream=stream)
+                    lap_fine=self._t(self.lap, l - 1, f_rows, 0) if dog else None, stream=stream)
 
-    def _down0(self, hb, mask, stream, which):
+    def _down0(self, hb, mask, stream, which, dog=True):
         """the first down step (level 0 -> 1) in three row bands: the interior band reads only rows this rank owns"""
         p = self.plan
         full = p.span(1, p.e[1])
@@ -583,12 +625,12 @@ class ShardedPyramid:
         lo = p.y0(1) + s if p.top else full[0]      # at the global image edge there is no ghost band
         hi = p.y1(1) - s if p.bot else full[1]
         if which == "interior":
-            self._down_region(hb, mask, 1, (lo, hi), stream)
+            self._down_region(hb, mask, 1, (lo, hi), stream, dog)
         else:
             if p.top:
-                self._down_region(hb, mask, 1, (full[0], lo), stream)
+                self._down_region(hb, mask, 1, (full[0], lo), stream, dog)
             if p.bot:
-                self._down_region(hb, mask, 1, (hi, full[1]), stream)
+                self._down_region(hb, mask, 1, (hi, full[1]), stream, dog)
 
     def down_sharded(self, hb, mask, stream=None, first=1):
         """way down through the sharded levels (needs the E0 ghost rows of gaus(0)); ends with this rank's rows of
@@ -599,7 +641,7 @@ class ShardedPyramid:
         for l in range(first, min(p.G, p.depth - 1) + 1):
             self._down_region(hb, mask, l, p.span(l, p.e[l]), stream)
 
-    def coarse_and_up(self, hb, mask, stream=None, fuse_coarse=False):
+    def coarse_and_up(self, hb, mask, stream=None, fuse_coarse=False, marks=None, wait_dog=False):
         """the replicated coarse levels (needs the gathered gaus(G)) and the whole way up: no communication"""
         p = self.plan
         first = 1 if p.world == 1 else p.G + 1
@@ -613,7 +655,13 @@ class ShardedPyramid:
             w0, w1 = p.width >> (l - 1), p.width >> l
             hb.pyr_down(self.gaus[l - 1][:, :w0], self.gaus[l][:, :w1], mask, lap_fine=self.lap[l - 1][:, :w0], stream=stream)
         for l in range(top_up, -1, -1):
+            if marks is not None and l == p.G - 1:
+                hb.timestamp(marks, 6, stream)
+            if marks is not None and l == 0:
+                hb.timestamp(marks, 7, stream)
             if l < p.G and p.world > 1:
+                if wait_dog:   # lap(l) comes from the DoG stream
+                    stream.wait_event(self._dog_ev[p.depth + l + 1])
                 f_rows = p.span(l, p.f[l])
                 c_rows = (f_rows[0] // 2, f_rows[1] // 2)
                 hb.pyr_up(self._t(self.gaus, l + 1, c_rows, 1), self._t(self.lap, l + 1, c_rows, 1),

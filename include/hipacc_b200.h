@@ -125,6 +125,9 @@ float hb_last_kernel_ms(void);
 /* launches issued by this library since process start (bench.py's gpu_launches) */
 long long hb_launch_count(void);
 int hb_stream_synchronize(void *stream);
+/* diagnostics: a one-thread kernel that writes the GPU's nanosecond %globaltimer into *slot_device (8 bytes) in stream
+ * order -- a timeline of the kernels of a captured pipeline, rank by rank (bench.py HB_BENCH_PHASES) */
+int hb_debug_timestamp(void *slot_device, void *stream);
 /* The stream a HipaccExecutionParameterCuda carries (runtime/hipacc_cu.hpp:234-245) is the user's cudaStream_t; host
  * code that does not include the CUDA headers creates one here (non-blocking with respect to the default stream). */
 int hb_stream_create(void **stream);
@@ -316,6 +319,15 @@ typedef struct {
   const float *coef_f32;
 } hb_pyr_down_desc;
 int hb_pyr_down(const hb_pyr_down_desc *desc, void *stream);
+
+/* DifferenceOfGaussian on its own (Gaussian_Laplacian_Pyramid/src/main.cpp:83-98 with an LF accessor): lap_fine =
+ * fine - LF(coarse).  hb_pyr_down with lap_fine.data == NULL followed by hb_pyr_dog equals the fused hb_pyr_down bit
+ * for bit; the split lets a sharded traversal run the DoG of a level in the shadow of the latency-bound coarse levels.
+ * `coarse` may declare ghost rows (row strips). */
+typedef struct {
+  hb_view fine, coarse, lap_fine;
+} hb_pyr_dog_desc;
+int hb_pyr_dog(const hb_pyr_dog_desc *desc, void *stream);
 
 typedef struct {
   hb_view coarse_gaus; /* gaus(l+1), read */
