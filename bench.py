@@ -667,20 +667,33 @@ def extra_operators(hb, dev, peak):
     import numpy as np
     import torch
     from hipacc_b200 import _abi as A, masks as M, specs as S, synth
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # a capturable stream: the timed launches replay as one CUDA graph
     res = {}
 
-    def timeit(fn, reps=10, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(reps):
-            fn()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+    def timeit(fn, reps=10, warm=3, graph=True):
+        """average device time of fn.  graph=True: `reps` launches are captured once and replayed as ONE CUDA graph, so a
+        short kernel (C1: 40 us) is not timed at the rate the Python host can enqueue it; blocking calls pass graph=False."""
+        torch.cuda.synchronize()   # the inputs were written on the default stream
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            run, n = fn, reps
+            if graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+                    for _ in range(reps):
+                        fn()
+                g.replay()
+                torch.cuda.synchronize()
+                run, n = g.replay, 3
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                run()
+            e1.record(stream)
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (n * reps if graph else n)
 
     def entry(name, px, alg_bytes, ms, note=""):
         gbs = alg_bytes / (ms * 1e-3) / 1e9
@@ -692,7 +705,15 @@ def extra_operators(hb, dev, peak):
     uo = hb.empty_image(A.U8, 4096, 4096, device=dev)
     g5 = S.gaussian_blur(M.GAUSS5, A.CLAMP)
     entry("C1_gaussian5x5_u8_4096", 4096 * 4096, 2 * 4096 * 4096, timeit(lambda: hb.local_op(g5, u, dst=uo, stream=stream)),
-          "bit-exact float mask: FP32-issue bound, 16 MiB image fits L2")
+          "bit-exact float mask: FP32-lane bound (25 separately rounded multiplies + 24 adds per pixel = 744 Gpx/s at 128 lanes/clk/SM); 16 MiB image, 3 waves of CTAs")
+    del u, uo
+    # the same operator on 16x the pixels: what the kernel sustains once the launch ramp and the last partial wave no longer weigh
+    u = hb.empty_image(A.U8, 16384, 16384, device=dev)
+    u.copy_(synth.image_torch("uint8", 16384, 16384, seed=1, device=dev))
+    uo = hb.empty_image(A.U8, 16384, 16384, device=dev)
+    entry("gaussian5x5_u8_16384", 16384 * 16384, 2 * 16384 * 16384, timeit(lambda: hb.local_op(g5, u, dst=uo, stream=stream)),
+          "C1's operator on a 16384^2 image (steady state)")
+    del u, uo
     # vector pixels: Gaussian_Blur_RGBA's own size, uchar4 (4 B read + 4 B written per pixel)
     rgba = torch.empty((3024, 4032, 4), dtype=torch.uint8, device=dev)
     rgba.view(3024, 4032 * 4).copy_(synth.image_torch("uint8", 4032 * 4, 3024, seed=6, device=dev))
@@ -731,9 +752,9 @@ def extra_operators(hb, dev, peak):
     del hs, ho
     # Reduction_Sum sample: int 4096 x 4096 (vectorised integer kernel, IDP-free for 32-bit pixels)
     it = torch.randint(-100, 100, (4096, 4096), dtype=torch.int32, device=dev)
-    entry("reduce_sum_s32_4096", 4096 * 4096, 4 * 4096 * 4096, timeit(lambda: hb.reduce(it, A.SUM, stream=stream)), "blocking call incl. the 16-byte result read-back")
+    entry("reduce_sum_s32_4096", 4096 * 4096, 4 * 4096 * 4096, timeit(lambda: hb.reduce(it, A.SUM, stream=stream), graph=False), "blocking call incl. the 16-byte result read-back")
     u8r = torch.randint(0, 255, (8192, 8192), dtype=torch.uint8, device=dev)
-    entry("reduce_sum_u8_8192", 8192 * 8192, 8192 * 8192, timeit(lambda: hb.reduce(u8r, A.SUM, stream=stream)), "IDP.4A byte sums; blocking call incl. read-back")
+    entry("reduce_sum_u8_8192", 8192 * 8192, 8192 * 8192, timeit(lambda: hb.reduce(u8r, A.SUM, stream=stream), graph=False), "IDP.4A byte sums; blocking call incl. read-back")
     return res
 
 

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int x = gxx[r][i] >> 4, y = gyy[r][i] >> 4;                       // non-negative: >> 4 == / 16
-            const int xy = (gxy[r][i] + ((gxy[r][i] >> 31) & 15)) >> 4;             // truncating / 16
+            const int xy = abs(gxy[r][i]) >> 4;                                     // |truncating / 16|: only xy * xy is used
             const float det = (float)(x * y - xy * xy);
             const float s = (float)(x + y);
             const float tr = __fmul_rn(__fmul_rn(p.k, s), s);

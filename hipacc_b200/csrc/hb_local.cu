@@ -356,19 +356,28 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     OpScope scope(s, "hb_local_op");
     int rc = HB_ERR_UNSUPPORTED;
     const int it = in.dtype, ot = out.dtype;
+    static int no_pair = -1;
+    if (no_pair < 0) { const char *e = getenv("HB_NO_PAIR"); no_pair = (e && atoi(e)) ? 1 : 0; }
+    const bool pair_ok = facc && fast && !no_pair;   // float SUM of products over every tap: two pixels per FMUL2 / FADD2
     if (x4) {
-        rc = facc ? launch_local_x4<float>(p, fast, s) : launch_local_x4<int>(p, fast, s);
+        if (pair_ok) rc = launch_local_pair(p, HB_U8, HB_U8, 4, s);
+        if (rc == HB_ERR_UNSUPPORTED) rc = facc ? launch_local_x4<float>(p, fast, s) : launch_local_x4<int>(p, fast, s);
         HB_REQUIRE(rc != HB_ERR_UNSUPPORTED, HB_ERR_UNSUPPORTED, "hb_local_op: uchar4 images support 3x3, 5x5 and 7x7 masks; no CPU fallback");
     } else if (facc) {
-        if (it == HB_U8 && ot == HB_U8) rc = launch_local<uchar, float, uchar>(p, fast, s);
-        else if (it == HB_F32 && ot == HB_F32) {
+        if (it == HB_U8 && ot == HB_U8) {
+            if (pair_ok) rc = launch_local_pair(p, it, ot, 1, s);
+            if (rc == HB_ERR_UNSUPPORTED) rc = launch_local<uchar, float, uchar>(p, fast, s);
+        } else if (it == HB_F32 && ot == HB_F32) {
             // hot path: persistent TMA-pipelined kernel (hb_local_tma.cu); anything it does not take runs staged
             // (the TMA kernel skips Domain holes itself: constexpr masks drop them, run-time masks are only taken when
             // every tap is visited)
             if (sum_of_products && d->epilogue == HB_EPI_CAST) rc = launch_local_tma_f32(p, visited == n, s);
+            if (rc == HB_ERR_UNSUPPORTED && pair_ok) rc = launch_local_pair(p, it, ot, 1, s);
             if (rc == HB_ERR_UNSUPPORTED) rc = launch_local<float, float, float>(p, fast, s);
+        } else if (it == HB_S8 && ot == HB_S8) {
+            if (pair_ok) rc = launch_local_pair(p, it, ot, 1, s);
+            if (rc == HB_ERR_UNSUPPORTED) rc = launch_local<signed char, float, signed char>(p, fast, s);
         }
-        else if (it == HB_S8 && ot == HB_S8) rc = launch_local<signed char, float, signed char>(p, fast, s);
     } else {
         // separable integer masks (Sobel 3x3 / 5x5 / 7x7, binomial Gaussians): two-pass variant, SX + SY instead of
         // SX * SY multiply-adds per pixel; exact because integer sums do not depend on the order

@@ -32,8 +32,8 @@ struct LocalParams {
     //   cpair[0][dy][dx] = c[dy][dx]      -> pairs (c0,c1) (c2,c3) ...   for pixels whose first tap sits in an even register
     //   cpair[1][dy][dx] = c[dy][dx + 1]  -> pairs (c1,c2) (c3,c4) ...   for the others
     //   cdup[k]          = (c[k], c[k])   -> one coefficient for two adjacent channel elements (uchar4 images)
-    float cpair[2][7][8];
-    float cdup[49][2];
+    alignas(16) float cpair[2][7][8];   // 16-byte aligned: a misaligned pair costs two uniform moves per use
+    alignas(16) float cdup[49][2];
 };
 
 // ---- arithmetic in the accumulation type (float: separately rounded mul / add) ----
@@ -113,5 +113,9 @@ template <> __device__ __forceinline__ int cval_of<int>(const LocalParams &p) { 
 // Returns HB_OK when it launched, HB_ERR_UNSUPPORTED when the operator / image is not eligible (caller falls
 // through to the staged kernels).
 int launch_local_tma_f32(const LocalParams &p, bool holes_allowed, cudaStream_t s);
+
+// hb_local_pair.cu: float SUM of products over every tap with packed multiplies and packed additions (two pixels per
+// FMUL2 / FADD2), 3x3 / 5x5 / 7x7.  dtypes after as_channels(); ch = 4 for uchar4 images.  HB_ERR_UNSUPPORTED = not taken.
+int launch_local_pair(const LocalParams &p, int in_dtype, int out_dtype, int ch, cudaStream_t s);
 
 }  // namespace hb

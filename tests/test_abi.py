@@ -102,3 +102,19 @@ def test_spec_fill_keeps_host_arrays_alive():
     spec.fill(d)
     assert d.size_x == 3 and d.epilogue == A.EPI_ADD_CAST and d.epi_p[0] == 0.5
     assert abs(d.coef_f32[4] - 1 / 9) < 1e-7 and not d.coef_s32
+
+
+def test_pair_kernel_sass_keeps_multiply_and_add_separately_rounded():
+    """hb_local_pair.cu's contract: FMUL2 + FADD2, never FFMA2 (ptxas contracts mul.rn.f32x2 -> add.rn.f32x2 unless the
+    product reaches the addition with its halves exchanged) -- a contracted product would round once instead of twice."""
+    import shutil
+    import subprocess
+    from hipacc_b200 import build as hb_build
+    hb_build.build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    obj = os.path.join(os.path.dirname(hb_build.LIB), "hb_local_pair.o")
+    sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, check=True).stdout
+    assert "FMUL2" in sass and "FADD2" in sass
+    assert "FFMA2" not in sass   # (scalar FFMA does appear: the correctly rounded division of the DIVF epilogue)
