@@ -130,9 +130,10 @@ def view(t, roi=None, ghost=(0, 0)):
     shape [H, W, 4] (uchar4 pixels, HB_U8X4; width / stride / roi count pixels)."""
     import torch
     if t.dim() == 3:
-        assert t.is_cuda and t.dtype == torch.uint8 and t.shape[2] == 4 and t.stride(2) == 1 and t.stride(1) == 4 and t.stride(0) % 4 == 0, \
-            "uchar4 images are uint8 CUDA tensors of shape [H, W, 4] with interleaved channels"
-        return A.make_view(t.data_ptr(), A.U8X4, t.shape[1], t.shape[0], t.stride(0) // 4, roi, ghost)
+        x4 = {torch.uint8: A.U8X4, torch.int8: A.S8X4, torch.int16: A.S16X4, torch.int32: A.S32X4, torch.float32: A.F32X4}
+        assert t.is_cuda and t.dtype in x4 and t.shape[2] == 4 and t.stride(2) == 1 and t.stride(1) == 4 and t.stride(0) % 4 == 0, \
+            "4-channel images (uchar4, char4, short4, int4, float4) are CUDA tensors of shape [H, W, 4] with interleaved channels"
+        return A.make_view(t.data_ptr(), x4[t.dtype], t.shape[1], t.shape[0], t.stride(0) // 4, roi, ghost)
     assert t.is_cuda and t.dim() == 2 and t.stride(1) == 1, "need a 2-D CUDA tensor with contiguous rows"
     return A.make_view(t.data_ptr(), _torch_dtype_map()[t.dtype], t.shape[1], t.shape[0], t.stride(0), roi, ghost)
 
@@ -207,7 +208,7 @@ def local_op(spec, src, dst=None, roi_in=None, roi_out=None, ghost=(0, 0), strea
     """Run a local operator (specs.LocalSpec) on CUDA tensors through hb_local_op."""
     import torch
     if dst is None:
-        dst = torch.zeros(src.shape, dtype=torch.uint8 if src.dim() == 3 else torch_dtype(spec.out_dtype), device=src.device)
+        dst = torch.zeros(src.shape, dtype=torch_dtype(spec.out_dtype), device=src.device)   # [H, W, 4] for 4-channel pixels
     d = A.hb_local_desc()
     spec.fill(d)
     d.in_ = view(src, roi_in, ghost)
@@ -234,7 +235,7 @@ def point_op(op, inputs, out_dtype=None, out_shape=None, interp=None, p=(0.0, 0.
     import torch
     if dst is None:
         shape = tuple(out_shape) if out_shape is not None else tuple(inputs[0].shape)
-        dst = torch.zeros(shape, dtype=torch.uint8 if inputs[0].dim() == 3 else torch_dtype(out_dtype), device=inputs[0].device)
+        dst = torch.zeros(shape, dtype=torch_dtype(out_dtype if out_dtype is not None else A.U8), device=inputs[0].device)
     d = A.hb_point_desc()
     d.n_in = len(inputs)
     for i, t in enumerate(inputs):

@@ -9,8 +9,8 @@ import ctypes as C
 # hb_status
 HB_OK, HB_ERR_INVALID, HB_ERR_UNSUPPORTED, HB_ERR_CUDA, HB_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 # hb_dtype
-U8, S8, U16, S16, S32, U32, F32, U8X4 = range(8)
-DTYPE_SIZE = {U8: 1, S8: 1, U16: 2, S16: 2, S32: 4, U32: 4, F32: 4, U8X4: 4}
+U8, S8, U16, S16, S32, U32, F32, U8X4, S8X4, U16X4, S16X4, S32X4, U32X4, F32X4 = range(14)
+DTYPE_SIZE = {U8: 1, S8: 1, U16: 2, S16: 2, S32: 4, U32: 4, F32: 4, U8X4: 4, S8X4: 4, U16X4: 8, S16X4: 8, S32X4: 16, U32X4: 16, F32X4: 16}
 DTYPE_NUMPY = {U8: "uint8", S8: "int8", U16: "uint16", S16: "int16", S32: "int32", U32: "uint32", F32: "float32"}
 NUMPY_DTYPE = {v: k for k, v in DTYPE_NUMPY.items()}
 # hb_boundary == hipacc::Boundary (dsl/image.hpp:46-52)

@@ -43,20 +43,34 @@ inline hb_view norm_view(const hb_view &v) {
     return o;
 }
 inline int dtype_size(int dt) {
-    switch (dt) { case HB_U8: case HB_S8: return 1; case HB_U16: case HB_S16: return 2; default: return 4; }  // HB_U8X4: 4 bytes per pixel
+    switch (dt) {
+    case HB_U8: case HB_S8: return 1;
+    case HB_U16: case HB_S16: return 2;
+    case HB_U16X4: case HB_S16X4: return 8;
+    case HB_S32X4: case HB_U32X4: case HB_F32X4: return 16;
+    default: return 4;   // 32-bit scalars, HB_U8X4, HB_S8X4
+    }
 }
 inline bool view_ok(const hb_view &v) {
-    return v.data && v.img_width > 0 && v.img_height > 0 && v.stride >= v.img_width && v.dtype >= HB_U8 && v.dtype <= HB_U8X4 &&
+    return v.data && v.img_width > 0 && v.img_height > 0 && v.stride >= v.img_width && v.dtype >= HB_U8 && v.dtype <= HB_DTYPE_LAST &&
            v.offset_x >= 0 && v.offset_y >= 0 && v.offset_x + v.width <= v.img_width && v.offset_y + v.height <= v.img_height &&
            v.ghost_top >= 0 && v.ghost_bottom >= 0 && v.offset_y - v.ghost_top >= 0 &&
            v.offset_y + v.height + v.ghost_bottom <= v.img_height;
 }
 
 // a uchar4 view as the uchar image of its channel elements (4x wider); `unit` = elements per pixel
+inline bool is_x4(int dt) { return dt >= HB_U8X4 && dt <= HB_F32X4; }
+inline int channel_dtype(int dt) {
+    switch (dt) {
+    case HB_U8X4: return HB_U8; case HB_S8X4: return HB_S8; case HB_U16X4: return HB_U16; case HB_S16X4: return HB_S16;
+    case HB_S32X4: return HB_S32; case HB_U32X4: return HB_U32; case HB_F32X4: return HB_F32;
+    default: return dt;
+    }
+}
 inline hb_view as_channels(const hb_view &v) {
     hb_view o = v;
-    if (v.dtype == HB_U8X4) {
-        o.dtype = HB_U8;
+    if (is_x4(v.dtype)) {
+        o.dtype = channel_dtype(v.dtype);
         o.img_width *= 4; o.stride *= 4; o.width *= 4; o.offset_x *= 4;
     }
     return o;

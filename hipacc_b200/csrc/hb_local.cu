@@ -206,15 +206,16 @@ __global__ void __launch_bounds__(256) local_generic_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// uchar4 images: the tiled kernel on the 4x wider channel-element image (p.* already in element units, p.win in pixels)
-template <typename TS>
+// 4-channel images (uchar4, float4, ...): the tiled kernel on the 4x wider channel-element image (p.* already in element
+// units, p.win in pixels)
+template <typename TI, typename TS, typename TO>
 static int launch_local_x4(const LocalParams &p, bool fast, cudaStream_t s) {
     dim3 block(BX, BY);
     dim3 grid((p.is_w + TW - 1) / TW, (p.is_h + TH - 1) / TH);
 #define HB_TILED4(SXV, SYV)                                                                        \
     if (p.size_x == SXV && p.size_y == SYV) {                                                      \
-        if (fast) local_tiled_kernel<uchar, TS, uchar, SXV, SYV, 0, 4><<<grid, block, 0, s>>>(p);  \
-        else local_tiled_kernel<uchar, TS, uchar, SXV, SYV, 1, 4><<<grid, block, 0, s>>>(p);       \
+        if (fast) local_tiled_kernel<TI, TS, TO, SXV, SYV, 0, 4><<<grid, block, 0, s>>>(p);        \
+        else local_tiled_kernel<TI, TS, TO, SXV, SYV, 1, 4><<<grid, block, 0, s>>>(p);             \
         g_launches++;                                                                              \
         return HB_OK;                                                                              \
     }
@@ -293,8 +294,8 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     HB_REQUIRE(d, HB_ERR_INVALID, "hb_local_op: null descriptor");
     hb_view in = norm_view(d->in), out = norm_view(d->out);
     HB_REQUIRE(view_ok(in) && view_ok(out), HB_ERR_INVALID, "hb_local_op: malformed view");
-    const bool x4 = in.dtype == HB_U8X4;
-    HB_REQUIRE(x4 == (out.dtype == HB_U8X4), HB_ERR_UNSUPPORTED, "hb_local_op: uchar4 input needs uchar4 output (and vice versa)");
+    const bool x4 = is_x4(in.dtype);
+    HB_REQUIRE(x4 == is_x4(out.dtype), HB_ERR_UNSUPPORTED, "hb_local_op: a 4-channel input needs a 4-channel output (and vice versa)");
     const int win_lo_x = in.offset_x, win_hi_x = in.offset_x + in.width;   // boundary window in PIXELS
     if (x4) { in = as_channels(in); out = as_channels(out); }              // everything else in channel elements
     HB_REQUIRE(d->size_x > 0 && d->size_y > 0 && (d->size_x & 1) && (d->size_y & 1) && d->size_x * d->size_y <= kMaxTaps &&
@@ -360,9 +361,16 @@ extern "C" int hb_local_op(const hb_local_desc *d, void *stream) {
     if (no_pair < 0) { const char *e = getenv("HB_NO_PAIR"); no_pair = (e && atoi(e)) ? 1 : 0; }
     const bool pair_ok = facc && fast && !no_pair;   // float SUM of products over every tap: two pixels per FMUL2 / FADD2
     if (x4) {
-        if (pair_ok) rc = launch_local_pair(p, HB_U8, HB_U8, 4, s);
-        if (rc == HB_ERR_UNSUPPORTED) rc = facc ? launch_local_x4<float>(p, fast, s) : launch_local_x4<int>(p, fast, s);
-        HB_REQUIRE(rc != HB_ERR_UNSUPPORTED, HB_ERR_UNSUPPORTED, "hb_local_op: uchar4 images support 3x3, 5x5 and 7x7 masks; no CPU fallback");
+        // element-wise per channel (dsl/types.hpp): uchar4 -> uchar4 (Gaussian / Laplace / Dilate / Box _RGBA), uchar4 -> int4 /
+        // short4 (Sobel_RGBA's intermediates), float4 -> float4
+        if (it == HB_U8 && ot == HB_U8) {
+            if (pair_ok) rc = launch_local_pair(p, HB_U8, HB_U8, 4, s);
+            if (rc == HB_ERR_UNSUPPORTED) rc = facc ? launch_local_x4<uchar, float, uchar>(p, fast, s) : launch_local_x4<uchar, int, uchar>(p, fast, s);
+        } else if (it == HB_U8 && ot == HB_S32 && !facc) rc = launch_local_x4<uchar, int, int>(p, fast, s);
+        else if (it == HB_U8 && ot == HB_S16 && !facc) rc = launch_local_x4<uchar, int, short>(p, fast, s);
+        else if (it == HB_F32 && ot == HB_F32 && facc) rc = launch_local_x4<float, float, float>(p, fast, s);
+        HB_REQUIRE(rc != HB_ERR_UNSUPPORTED, HB_ERR_UNSUPPORTED,
+                   "hb_local_op: 4-channel images support 3x3, 5x5 and 7x7 masks on uchar4 -> uchar4 / short4 / int4 and float4 -> float4; no CPU fallback");
     } else if (facc) {
         if (it == HB_U8 && ot == HB_U8) {
             if (pair_ok) rc = launch_local_pair(p, it, ot, 1, s);

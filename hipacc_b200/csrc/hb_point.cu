@@ -213,18 +213,18 @@ extern "C" int hb_point_op(const hb_point_desc *d, void *stream) {
     HB_REQUIRE(d && d->n_in >= 1 && d->n_in <= 3, HB_ERR_INVALID, "hb_point_op: bad descriptor");
     hb_view out = norm_view(d->out);
     HB_REQUIRE(view_ok(out), HB_ERR_INVALID, "hb_point_op: malformed output view");
-    const bool x4 = out.dtype == HB_U8X4;   // element-wise on the channels (dsl/types.hpp vector operators)
+    const bool x4 = is_x4(out.dtype);   // element-wise on the channels (dsl/types.hpp vector operators)
     if (x4) out = as_channels(out);
     PointParams p;
     memset(&p, 0, sizeof(p));
-    const int it = x4 ? (int)HB_U8 : d->in[0].dtype;
+    const int it = channel_dtype(d->in[0].dtype);
     const size_t ies = dtype_size(it), oes = dtype_size(out.dtype);
     bool vec = (out.stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out.data) + (size_t)out.offset_x * oes) % (4 * oes) == 0);
     for (int k = 0; k < d->n_in; ++k) {
         hb_view v = norm_view(d->in[k]);
         if (x4) {
-            HB_REQUIRE(v.dtype == HB_U8X4 && d->interp[k] == HB_INTERP_NO && d->op != HB_POINT_HARRIS, HB_ERR_UNSUPPORTED,
-                       "hb_point_op: uchar4 operands must all be uchar4 and not interpolated; no CPU fallback");
+            HB_REQUIRE(is_x4(v.dtype) && d->interp[k] == HB_INTERP_NO && d->op != HB_POINT_HARRIS, HB_ERR_UNSUPPORTED,
+                       "hb_point_op: the operands of a 4-channel operator must all be 4-channel images and not interpolated; no CPU fallback");
             v = as_channels(v);
         }
         HB_REQUIRE(view_ok(v) && v.dtype == it, HB_ERR_INVALID, "hb_point_op: malformed input view %d (all inputs share one pixel type)", k);

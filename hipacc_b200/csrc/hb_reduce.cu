@@ -426,7 +426,7 @@ extern "C" int hb_reduce(const hb_view *in_, int mode, void *result_host, void *
         return rc;
     }
     HB_REQUIRE(!stream_is_capturing(s), HB_ERR_INVALID, "hb_reduce blocks and cannot be captured");
-    HB_REQUIRE(v.dtype != HB_U8X4, HB_ERR_UNSUPPORTED, "hb_reduce: vector pixels have no device reduction; no CPU fallback");
+    HB_REQUIRE(!is_x4(v.dtype), HB_ERR_UNSUPPORTED, "hb_reduce: vector pixels have no device reduction; no CPU fallback");
     Scratch *sc = nullptr;
     int rc = get_scratch(&sc, s);
     if (rc) return rc;

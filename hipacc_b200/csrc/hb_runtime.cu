@@ -230,7 +230,7 @@ int hb_stream_destroy(void *stream) {
 }
 
 int hb_image_create(int dtype, int width, int height, int alignment, hb_view *out) {
-    HB_REQUIRE(out && width > 0 && height > 0 && dtype >= HB_U8 && dtype <= HB_U8X4, HB_ERR_INVALID, "hb_image_create: bad arguments");
+    HB_REQUIRE(out && width > 0 && height > 0 && dtype >= HB_U8 && dtype <= HB_DTYPE_LAST, HB_ERR_INVALID, "hb_image_create: bad arguments");
     const int es = dtype_size(dtype);
     if (alignment <= 0) alignment = 256;
     // alignment has to be a multiple of sizeof(T) (runtime/hipacc_cu.tpp:54-57)

@@ -41,9 +41,14 @@ typedef enum {  /* pixel / accumulator types */
   HB_U8 = 0, HB_S8 = 1, HB_U16 = 2, HB_S16 = 3, HB_S32 = 4, HB_U32 = 5, HB_F32 = 6,
   /* vector pixel (dsl/types.hpp:56-516): uchar4 = 4 interleaved uchar channels (RGBA); width / stride / offsets count
    * PIXELS.  Local and point operators treat the channels independently, which is what the DSL's element-wise
-   * float4 / int4 arithmetic and convert_uchar4() do (samples-public/1_Local_Operators/*_RGBA). */
-  HB_U8X4 = 7
+   * float4 / int4 arithmetic and convert_uchar4() do (samples-public/1_Local_Operators, the _RGBA samples). */
+  HB_U8X4 = 7,
+  /* the other 4-channel pixel types of dsl/types.hpp (char4, ushort4, short4, int4, uint4, float4): images of these types
+   * can be created, copied, read and written, are the intermediates of the RGBA pipelines (Sobel_RGBA: short4 / int4) and
+   * are what kernels compiled from a kernel() body (include/hipacc_b200/hipacc.hpp under nvcc) operate on. */
+  HB_S8X4 = 8, HB_U16X4 = 9, HB_S16X4 = 10, HB_S32X4 = 11, HB_U32X4 = 12, HB_F32X4 = 13
 } hb_dtype;
+#define HB_DTYPE_LAST HB_F32X4
 
 typedef enum {  /* hipacc::Boundary, dsl/image.hpp:46-52 */
   HB_BOUNDARY_UNDEFINED = 0, HB_BOUNDARY_CLAMP = 1, HB_BOUNDARY_REPEAT = 2,

@@ -6,21 +6,38 @@
 // (accessors hold references, execute() is idempotent per Kernel object), same enum values.
 //
 // What differs, and why: in the reference a Kernel's `kernel()` body is compiled -- by the host compiler in
-// DSL mode, by Hipacc's Clang-based rewriter into a CUDA kernel otherwise (lib/AST/ASTTranslate.cpp).  This
-// front ships pre-built sm_100a kernels instead of a compiler, so a Kernel subclass states its operator as a
-// value: it overrides `lower()` and returns one of the b200:: descriptions below -- exactly the facts
-// Hipacc's KernelStatistics / Convolution passes extract from the body (lib/Analysis/KernelStatistics.cpp,
-// lib/AST/Convolution.cpp).  `kernel()` stays in the class as the definition of the semantics (it compiles
-// against this header, it is never run on the host: there is no CPU fallback).  A Kernel without a lowering,
-// or with one the library has no device kernel for, fails loudly.
+// DSL mode, by Hipacc's Clang-based rewriter into a CUDA kernel otherwise (lib/AST/ASTTranslate.cpp).  Here an
+// operator reaches the device in one of two ways:
+//
+//   lower()   (host compiler or nvcc)  the Kernel subclass states its operator as a value -- one of the b200::
+//             descriptions below, exactly the facts Hipacc's KernelStatistics / Convolution passes extract from the
+//             body (lib/Analysis/KernelStatistics.cpp, lib/AST/Convolution.cpp) -- and execute() launches the
+//             library's pre-built, hand-tuned sm_100a kernel for it (the hot path of every BASELINE config);
+//   kernel()  (translation unit compiled by nvcc, `-x cu`)  the body itself is compiled for the device: every
+//             DSL form it may use (output(), x(), y(), Accessor / Mask / Domain calls, convolve / reduce / iterate,
+//             the vector types) is a __host__ __device__ function of this header, and execute() launches
+//             dsl_kernel<YourKernel>, one thread per pixel of the iteration space.  Any body runs this way -- no
+//             lower() needed -- which is what the reference's ASTTranslate does with a compiler and this header does
+//             with templates.  Sample sources compile unmodified: the macro at the end of this header makes the
+//             member `kernel()` __host__ __device__ and adds the typed launch hook to the class.
+//
+// With both present, lower() wins (it is the tuned kernel) and HIPACC_B200_CHECK_LOWERING=1 runs the compiled
+// body next to it and aborts on any difference -- a lower() that no longer matches an edited body is caught.
+// A body is never run on the HOST: a Kernel with neither a lowering nor a device-compiled body fails loudly.
 #ifndef HIPACC_B200_DSL_HPP
 #define HIPACC_B200_DSL_HPP
 
 #include <algorithm>
 #include <cmath>
 #include <initializer_list>
+#include <type_traits>
 
 #include "hipacc_rt.hpp"
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define HIPACC_B200_DEVICE_DSL 1
+#endif
 
 #ifndef HIPACC_CODEGEN
 #define HIPACC_CODEGEN
@@ -33,23 +50,106 @@ enum class Interpolate : uint8_t { NO = 0, NN, LF, B5, CF, L3 };                
 enum class Reduce : uint8_t { SUM = 0, MIN, MAX, PROD, MEDIAN };                   // dsl/kernel.hpp:48-54
 
 namespace math {
-template <typename T> inline T min(T a, T b) { return b < a ? b : a; }
-template <typename T> inline T max(T a, T b) { return b > a ? b : a; }
+template <typename T, typename std::enable_if<!hipacc_b200::vec4<T>::is, int>::type = 0> HB_HD T min(T a, T b) { return b < a ? b : a; }
+template <typename T, typename std::enable_if<!hipacc_b200::vec4<T>::is, int>::type = 0> HB_HD T max(T a, T b) { return b > a ? b : a; }
+using hipacc_b200::vmath::min;   // element-wise on the vector types, vector or scalar bound (dsl/math_functions.hpp)
+using hipacc_b200::vmath::max;
 using std::abs; using std::exp; using std::sqrt;
-using ::expf; using ::sqrtf; using ::fabsf;  // the C library's float functions, as in dsl/math_functions.hpp
+using ::expf; using ::sqrtf; using ::fabsf; using ::powf;  // the C library's float functions, as in dsl/math_functions.hpp
+#define HB_VEC_FUN1(NAME) HB_HD float4 NAME(float4 v) { return make_float4(::NAME(v.x), ::NAME(v.y), ::NAME(v.z), ::NAME(v.w)); }
+HB_VEC_FUN1(sqrtf) HB_VEC_FUN1(expf) HB_VEC_FUN1(fabsf)
+#undef HB_VEC_FUN1
 }  // namespace math
 
 namespace b200 {
 [[noreturn]] inline void host_body_called() {
     std::fprintf(stderr, "hipacc_b200: a kernel() body was executed on the host; this front runs operators on the device only "
-                         "(override lower(), see include/hipacc_b200/hipacc.hpp)\n");
+                         "(override lower(), or compile the translation unit with nvcc; see include/hipacc_b200/hipacc.hpp)\n");
     std::abort();
 }
+
+// ---------------------------------------------------------------------------------------------------
+// device side of the compiled-body path (only what device code of this header touches)
+// ---------------------------------------------------------------------------------------------------
+namespace dev {
+constexpr int kSlots = 8;          // Mask / Domain objects one kernel() body may iterate
+constexpr int kBlockX = 32, kBlockY = 8;
+
+#ifdef __CUDACC__
+// position of this thread in the iteration space
+__device__ __forceinline__ int gx() { return (int)(blockIdx.x * kBlockX + threadIdx.x); }
+__device__ __forceinline__ int gy() { return (int)(blockIdx.y * kBlockY + threadIdx.y); }
+// the current offset of a Mask / Domain iteration (convolve / reduce / iterate set it, mask() / in(mask) read it) is
+// per-thread state of an object that all threads share: it lives in shared memory, one cell per (object, thread)
+__device__ __forceinline__ int &iter_state(int slot) {
+    __shared__ int cells[kSlots][kBlockX * kBlockY];
+    return cells[slot][threadIdx.y * kBlockX + threadIdx.x];
+}
+#endif
+
+// index remapping of a boundary mode on [lo, hi) (dsl/image.hpp:574-612; decisions of SURVEY.md 8c: REPEAT wraps with
+// `while`, upper test first) -- the same function the library's tile loaders apply (csrc/hb_common.cuh)
+HB_HD int remap(int idx, int lo, int hi, Boundary mode) {
+    switch (mode) {
+    case Boundary::CLAMP:
+        if (idx >= hi) idx = hi - 1;
+        if (idx < lo) idx = lo;
+        break;
+    case Boundary::MIRROR:
+        if (idx >= hi) idx = hi - (idx + 1 - hi);
+        if (idx < lo) idx = lo + (lo - idx - 1);
+        break;
+    case Boundary::REPEAT: {
+        const int n = hi - lo;
+        while (idx >= hi) idx -= n;
+        while (idx < lo) idx += n;
+        break;
+    }
+    default: break;
+    }
+    return idx;
+}
+
+// host side: live DSL objects a kernel() body may reference; a launch copies the ones the Kernel object points to
+// into device memory and redirects the pointers (see launch_generic)
+struct Arena;
+struct Obj {
+    const void *host;
+    size_t size;
+    void (*prepare)(const void *host_obj, size_t snapshot_at, Arena &arena);   // fills the device-side fields of the copy at arena.bytes[snapshot_at]
+};
+inline std::vector<Obj> &registry() { static std::vector<Obj> r; return r; }
+inline void enroll(const void *p, size_t n, void (*prep)(const void *, size_t, Arena &)) { registry().push_back(Obj{p, n, prep}); }
+inline void retire(const void *p) {
+    auto &r = registry();
+    for (size_t i = r.size(); i-- > 0;)
+        if (r[i].host == p) { r.erase(r.begin() + (long)i); return; }
+}
+// bytes that go to the device with one launch: object snapshots, coefficient tables, domain bitmaps.  Pointers into the
+// arena are kept as offsets (+ 1, so that 0 stays null) in `fixups` until the device address is known.
+struct Arena {
+    std::vector<unsigned char> bytes;
+    std::vector<size_t> fixups;   // offsets (within bytes) of pointer fields holding (arena offset + 1)
+    int next_slot = 0;
+    size_t put(const void *src, size_t n, size_t align = 16) {
+        const size_t at = (bytes.size() + align - 1) / align * align;
+        bytes.resize(at + n);
+        if (src) std::memcpy(bytes.data() + at, src, n);
+        return at;
+    }
+};
+struct LaunchCtx {
+    void *stream;
+    void *out_override;   // non-null: write the result here instead of the iteration space's image (lowering check)
+    bool *launched;       // set when a device-compiled body exists and was launched
+};
+}  // namespace dev
 }  // namespace b200
 
 // ---------------------------------------------------------------------------------------------------
 // Image (dsl/image.hpp:64-214): pixels live in HBM; data() reads them back into the internal host mirror
 // ---------------------------------------------------------------------------------------------------
+template <typename data_t> class Accessor;
 template <typename data_t> class Image {
     HipaccImageCuda<data_t> mem_;
 
@@ -66,6 +166,8 @@ template <typename data_t> class Image {
         else mem_ = other.mem_;
         return *this;
     }
+    // img = acc: copy the accessor's region into this image (dsl/image.hpp:150-160; sizes must match)
+    Image &operator=(const Accessor<data_t> &other);
     Image(const Image &) = default;
     data_t *data() { return hipaccReadMemory(mem_); }
     const HipaccImageCuda<data_t> &mem() const { return mem_; }
@@ -77,18 +179,54 @@ template <typename data_t> class Image {
 class MaskBase {
   protected:
     int size_x_, size_y_;
-    std::vector<uchar> domain_;  // row-major, 1 = visited
+    std::vector<uchar> domain_;  // row-major, 1 = visited (host)
+    // device-side fields, valid in the snapshot a launch makes
+    const uchar *d_domain_ = nullptr;
+    int d_slot_ = 0;
+
+    static void prepare_base(const MaskBase &m, size_t snap_at, b200::dev::Arena &a) {
+        const size_t at = a.put(m.domain_.data(), m.domain_.size(), 16);
+        MaskBase &snap = *reinterpret_cast<MaskBase *>(a.bytes.data() + snap_at);   // after put(): it may move the buffer
+        snap.d_domain_ = reinterpret_cast<const uchar *>(at + 1);
+        a.fixups.push_back(snap_at + (size_t)((const unsigned char *)&snap.d_domain_ - (const unsigned char *)&snap));
+        snap.d_slot_ = a.next_slot++;
+        if (snap.d_slot_ >= b200::dev::kSlots) {
+            std::fprintf(stderr, "hipacc_b200: a kernel() body may reference at most %d Mask / Domain objects\n", b200::dev::kSlots);
+            std::abort();
+        }
+    }
+    static void prepare(const void *host_obj, size_t snap_at, b200::dev::Arena &a) {
+        prepare_base(*static_cast<const MaskBase *>(host_obj), snap_at, a);
+    }
 
   public:
     MaskBase(int size_x, int size_y) : size_x_(size_x), size_y_(size_y), domain_((size_t)size_x * size_y, 1) {
         assert(size_x > 0 && size_y > 0 && "Size for Domain must be positive!");
     }
+    MaskBase(const MaskBase &o) : size_x_(o.size_x_), size_y_(o.size_y_), domain_(o.domain_) {}
     virtual ~MaskBase() = default;
-    int size_x() const { return size_x_; }
-    int size_y() const { return size_y_; }
+    HB_HD int size_x() const { return size_x_; }
+    HB_HD int size_y() const { return size_y_; }
     const std::vector<uchar> &domain_bits() const { return domain_; }
-    int x() const { b200::host_body_called(); }
-    int y() const { b200::host_body_called(); }
+    // offset of the current iteration step relative to the centre (dsl/mask.hpp:100-110)
+    HB_HD int x() const {
+#ifdef __CUDA_ARCH__
+        return (short)(b200::dev::iter_state(d_slot_) & 0xffff);
+#else
+        b200::host_body_called();
+#endif
+    }
+    HB_HD int y() const {
+#ifdef __CUDA_ARCH__
+        return b200::dev::iter_state(d_slot_) >> 16;
+#else
+        b200::host_body_called();
+#endif
+    }
+#ifdef __CUDA_ARCH__
+    __device__ __forceinline__ void dev_seek(int dx, int dy) const { b200::dev::iter_state(d_slot_) = (dy << 16) | (dx & 0xffff); }
+    __device__ __forceinline__ bool dev_visited(int k) const { return d_domain_[k] != 0; }
+#endif
 };
 
 class Domain : public MaskBase {
@@ -99,12 +237,15 @@ class Domain : public MaskBase {
         explicit Setter(uchar &r) : ref_(r) {}
         Setter &operator=(const uchar val) { ref_ = val ? 1 : 0; return *this; }
     };
-    Domain(const int size_x, const int size_y) : MaskBase(size_x, size_y) {}
+    Domain(const int size_x, const int size_y) : MaskBase(size_x, size_y) { b200::dev::enroll(this, sizeof(*this), &MaskBase::prepare); }
     template <int size_y, int size_x> explicit Domain(const uchar (&domain)[size_y][size_x]) : MaskBase(size_x, size_y) {
         for (int y = 0; y < size_y; ++y)
             for (int x = 0; x < size_x; ++x) domain_[(size_t)y * size_x + x] = domain[y][x] ? 1 : 0;
+        b200::dev::enroll(this, sizeof(*this), &MaskBase::prepare);
     }
-    explicit Domain(const MaskBase &mask) : MaskBase(mask) {}
+    explicit Domain(const MaskBase &mask) : MaskBase(mask) { b200::dev::enroll(this, sizeof(*this), &MaskBase::prepare); }
+    Domain(const Domain &o) : MaskBase(o) { b200::dev::enroll(this, sizeof(*this), &MaskBase::prepare); }
+    ~Domain() override { b200::dev::retire(this); }
     // dom(xf, yf) = 0 punches a hole; offsets are relative to the centre (dsl/mask.hpp:186-190)
     Setter operator()(const int xf, const int yf) {
         return Setter(domain_.at((size_t)(yf + size_y_ / 2) * size_x_ + (xf + size_x_ / 2)));
@@ -117,9 +258,18 @@ class Domain : public MaskBase {
 
 template <typename data_t> class Mask : public MaskBase {
     std::vector<data_t> coef_;
+    const data_t *d_coef_ = nullptr;   // device side (snapshot)
 
     void sync_domain() {  // zero coefficients are Domain holes (Mask ctor, dsl/mask.hpp:238-250)
         for (size_t i = 0; i < coef_.size(); ++i) domain_[i] = coef_[i] != data_t(0) ? 1 : 0;
+    }
+    static void prepare(const void *host_obj, size_t snap_at, b200::dev::Arena &a) {
+        const Mask &m = *static_cast<const Mask *>(host_obj);
+        const size_t at = a.put(m.coef_.data(), m.coef_.size() * sizeof(data_t), 16);
+        Mask &snap = *reinterpret_cast<Mask *>(a.bytes.data() + snap_at);   // after put(): it may move the buffer
+        snap.d_coef_ = reinterpret_cast<const data_t *>(at + 1);
+        a.fixups.push_back(snap_at + (size_t)((const unsigned char *)&snap.d_coef_ - (const unsigned char *)&snap));
+        MaskBase::prepare_base(m, snap_at, a);
     }
 
   public:
@@ -127,8 +277,12 @@ template <typename data_t> class Mask : public MaskBase {
         for (int y = 0; y < size_y; ++y)
             for (int x = 0; x < size_x; ++x) coef_[(size_t)y * size_x + x] = mask[y][x];
         sync_domain();
+        b200::dev::enroll(this, sizeof(*this), &Mask::prepare);
     }
-    Mask(int size_x, int size_y) : MaskBase(size_x, size_y), coef_((size_t)size_x * size_y) {}
+    Mask(int size_x, int size_y) : MaskBase(size_x, size_y), coef_((size_t)size_x * size_y) { b200::dev::enroll(this, sizeof(*this), &Mask::prepare); }
+    Mask(const Mask &o) : MaskBase(o), coef_(o.coef_) { b200::dev::enroll(this, sizeof(*this), &Mask::prepare); }
+    ~Mask() override { b200::dev::retire(this); }
+    // run-time coefficients (dsl/mask.hpp:252-262): the device copy is refreshed at every launch
     Mask &operator=(const data_t *other) {
         std::copy(other, other + coef_.size(), coef_.begin());
         sync_domain();
@@ -136,9 +290,27 @@ template <typename data_t> class Mask : public MaskBase {
     }
     const std::vector<data_t> &coefficients() const { return coef_; }
     // kernel()-body forms: mask(), mask(dom), mask(x, y)
-    data_t operator()() const { b200::host_body_called(); }
-    data_t operator()(const Domain &) const { b200::host_body_called(); }
-    data_t operator()(int, int) const { b200::host_body_called(); }
+    HB_HD data_t operator()() const {
+#ifdef __CUDA_ARCH__
+        return d_coef_[(y() + size_y_ / 2) * size_x_ + x() + size_x_ / 2];
+#else
+        b200::host_body_called();
+#endif
+    }
+    HB_HD data_t operator()(const Domain &dom) const {
+#ifdef __CUDA_ARCH__
+        return d_coef_[(dom.y() + size_y_ / 2) * size_x_ + dom.x() + size_x_ / 2];
+#else
+        (void)dom; b200::host_body_called();
+#endif
+    }
+    HB_HD data_t operator()(int xf, int yf) const {
+#ifdef __CUDA_ARCH__
+        return d_coef_[(yf + size_y_ / 2) * size_x_ + xf + size_x_ / 2];
+#else
+        (void)xf; (void)yf; b200::host_body_called();
+#endif
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -171,6 +343,20 @@ class AccessorBase {
 };
 
 template <typename data_t> class Accessor : public AccessorBase {
+    // device-side fields, valid in the snapshot a launch makes
+    data_t *d_ptr_ = nullptr;
+    int d_stride_ = 0, d_iw_ = 0, d_ih_ = 0;
+    data_t d_const_{};
+
+    static void prepare(const void *host_obj, size_t snap_at, b200::dev::Arena &arena) {
+        const Accessor &a = *static_cast<const Accessor *>(host_obj);
+        Accessor &snap = *reinterpret_cast<Accessor *>(arena.bytes.data() + snap_at);
+        const hb_view &v = a.img.mem()->get_view();
+        snap.d_ptr_ = static_cast<data_t *>(v.data);
+        snap.d_stride_ = v.stride; snap.d_iw_ = v.img_width; snap.d_ih_ = v.img_height;
+        snap.d_const_ = a.const_val;
+    }
+
   public:
     Image<data_t> &img;
     const int width_, height_, offset_x_, offset_y_;
@@ -181,28 +367,105 @@ template <typename data_t> class Accessor : public AccessorBase {
 
     Accessor(Image<data_t> &Img, const Interpolate imode = Interpolate::NO)
         : img(Img), width_(Img.width()), height_(Img.height()), offset_x_(0), offset_y_(0), bmode(Boundary::CLAMP), const_val(), imode(imode),
-          has_bc(false) {}
+          has_bc(false) { b200::dev::enroll(this, sizeof(*this), &Accessor::prepare); }
     Accessor(Image<data_t> &Img, const int width, const int height, const int xf, const int yf, const Interpolate imode = Interpolate::NO)
-        : img(Img), width_(width), height_(height), offset_x_(xf), offset_y_(yf), bmode(Boundary::CLAMP), const_val(), imode(imode), has_bc(false) {}
+        : img(Img), width_(width), height_(height), offset_x_(xf), offset_y_(yf), bmode(Boundary::CLAMP), const_val(), imode(imode), has_bc(false) {
+        b200::dev::enroll(this, sizeof(*this), &Accessor::prepare);
+    }
     Accessor(const BoundaryCondition<data_t> &BC, const Interpolate imode = Interpolate::NO)
         : img(BC.img), width_(BC.img.width()), height_(BC.img.height()), offset_x_(0), offset_y_(0), bmode(BC.mode), const_val(BC.const_val),
-          imode(imode), has_bc(true) {}
+          imode(imode), has_bc(true) { b200::dev::enroll(this, sizeof(*this), &Accessor::prepare); }
     Accessor(const BoundaryCondition<data_t> &BC, const int width, const int height, const int xf, const int yf,
              const Interpolate imode = Interpolate::NO)
         : img(BC.img), width_(width), height_(height), offset_x_(xf), offset_y_(yf), bmode(BC.mode), const_val(BC.const_val), imode(imode),
-          has_bc(true) {}
+          has_bc(true) { b200::dev::enroll(this, sizeof(*this), &Accessor::prepare); }
+    Accessor(const Accessor &o)
+        : img(o.img), width_(o.width_), height_(o.height_), offset_x_(o.offset_x_), offset_y_(o.offset_y_), bmode(o.bmode), const_val(o.const_val),
+          imode(o.imode), has_bc(o.has_bc) { b200::dev::enroll(this, sizeof(*this), &Accessor::prepare); }
+    ~Accessor() override { b200::dev::retire(this); }
 
-    int width() const { return width_; }
-    int height() const { return height_; }
+    HB_HD int width() const { return width_; }
+    HB_HD int height() const { return height_; }
     HipaccAccessor<data_t> rt() const { return HipaccAccessor<data_t>(img.mem(), (size_t)width_, (size_t)height_, offset_x_, offset_y_); }
 
-    // kernel()-body forms
-    data_t &operator()() { b200::host_body_called(); }
-    data_t &operator()(const int, const int) { b200::host_body_called(); }
-    data_t &operator()(const MaskBase &) { b200::host_body_called(); }
-    int x() const { b200::host_body_called(); }
-    int y() const { b200::host_body_called(); }
+    // acc = img / acc = other: region copies on the device (dsl/image.hpp:657-680; sizes must match)
+    Accessor &operator=(const Image<data_t> &other) {
+        assert(width_ == other.width() && height_ == other.height() && "Size of Accessor and Image have to be the same!");
+        hipaccCopyMemoryRegion(HipaccAccessor<data_t>(other.mem()), rt());
+        return *this;
+    }
+    Accessor &operator=(const Accessor &other) {
+        assert(width_ == other.width_ && height_ == other.height_ && "Accessor sizes have to be the same!");
+        hipaccCopyMemoryRegion(other.rt(), rt());
+        return *this;
+    }
+
+#ifdef __CUDA_ARCH__
+    // pixel (IS-relative position + offset) through the boundary mode of this accessor's region
+    __device__ __forceinline__ data_t &dev_fetch(int dx, int dy) const {
+        int x = offset_x_ + b200::dev::gx() + dx, y = offset_y_ + b200::dev::gy() + dy;
+        if (bmode == Boundary::CONSTANT) {
+            if (x < offset_x_ || x >= offset_x_ + width_ || y < offset_y_ || y >= offset_y_ + height_) return const_cast<data_t &>(d_const_);
+        } else if (bmode != Boundary::UNDEFINED) {
+            x = b200::dev::remap(x, offset_x_, offset_x_ + width_, bmode);
+            y = b200::dev::remap(y, offset_y_, offset_y_ + height_, bmode);
+        }
+        x = x < 0 ? 0 : x >= d_iw_ ? d_iw_ - 1 : x;   // memory safety for UNDEFINED / degenerate regions
+        y = y < 0 ? 0 : y >= d_ih_ ? d_ih_ - 1 : y;
+        return d_ptr_[(size_t)y * d_stride_ + x];
+    }
+#endif
+    // kernel()-body forms (interpolating accessors are served by the lowered point operators only)
+    HB_HD data_t &operator()() {
+#ifdef __CUDA_ARCH__
+        return dev_fetch(0, 0);
+#else
+        b200::host_body_called();
+#endif
+    }
+    HB_HD data_t &operator()(const int xf, const int yf) {
+#ifdef __CUDA_ARCH__
+        return dev_fetch(xf, yf);
+#else
+        (void)xf; (void)yf; b200::host_body_called();
+#endif
+    }
+    HB_HD data_t &operator()(const MaskBase &m) {
+#ifdef __CUDA_ARCH__
+        return dev_fetch(m.x(), m.y());
+#else
+        (void)m; b200::host_body_called();
+#endif
+    }
+    // x and y refer to the area defined by the Accessor (dsl/image.hpp:683-690)
+    HB_HD data_t &pixel_at(const int x, const int y) {
+#ifdef __CUDA_ARCH__
+        return d_ptr_[(size_t)(y + offset_y_) * d_stride_ + x + offset_x_];
+#else
+        (void)x; (void)y; b200::host_body_called();
+#endif
+    }
+    HB_HD int x() const {
+#ifdef __CUDA_ARCH__
+        return b200::dev::gx();
+#else
+        b200::host_body_called();
+#endif
+    }
+    HB_HD int y() const {
+#ifdef __CUDA_ARCH__
+        return b200::dev::gy();
+#else
+        b200::host_body_called();
+#endif
+    }
 };
+
+template <typename data_t> Image<data_t> &Image<data_t>::operator=(const Accessor<data_t> &other) {
+    assert(width() == other.width() && height() == other.height() && "Size of Image and Accessor have to be the same!");
+    hipaccCopyMemoryRegion(other.rt(), HipaccAccessor<data_t>(mem_));
+    return *this;
+}
 
 template <typename data_t> class IterationSpace {
   public:
@@ -248,12 +511,18 @@ struct Lowering {
     std::function<void(const hb_view &out, void *stream)> launch;
 };
 
+// HIPACC_B200_CHECK_LOWERING: integers and bytes must be identical; float pipelines agree within 1e-5 relative (the
+// contract of BASELINE.json: the compiled body may contract a * b + c, the library kernels never do)
+inline bool pixels_agree(float a, float b) { const float d = a > b ? a - b : b - a, m = (a < 0 ? -a : a) > (b < 0 ? -b : b) ? (a < 0 ? -a : a) : (b < 0 ? -b : b); return a == b || d <= 1e-5f * m + 1e-30f; }
+template <typename T, typename std::enable_if<std::is_integral<T>::value, int>::type = 0> inline bool pixels_agree(T a, T b) { return a == b; }
+template <typename V, hipacc_b200::if_vec<V> = 0> inline bool pixels_agree(const V &a, const V &b) {
+    return pixels_agree(a.x, b.x) && pixels_agree(a.y, b.y) && pixels_agree(a.z, b.z) && pixels_agree(a.w, b.w);
+}
+
 namespace detail {
 // boundary constant as the C ABI carries it (a scalar; vector pixels: the x channel, broadcast)
-template <typename T> inline double const_of(const T &v) { return (double)v; }
-#ifndef HIPACC_B200_NO_VECTOR_TYPES
-inline double const_of(const uchar4 &v) { return (double)v.x; }
-#endif
+template <typename T, typename std::enable_if<!hipacc_b200::vec4<T>::is, int>::type = 0> inline double const_of(const T &v) { return (double)v; }
+template <typename V, hipacc_b200::if_vec<V> = 0> inline double const_of(const V &v) { return (double)v.x; }
 template <typename T> hb_view in_view(const Accessor<T> &a) { return a.rt().view(); }
 inline int mode_of(Reduce m) { assert(m != Reduce::MEDIAN && "MEDIAN is not implemented"); return (int)m; }
 
@@ -357,11 +626,102 @@ inline Lowering harris(const Accessor<uchar> &in, float k, float threshold) {
 // ---------------------------------------------------------------------------------------------------
 // Kernel (dsl/kernel.hpp:56-330)
 // ---------------------------------------------------------------------------------------------------
+namespace b200 { namespace dev {
+#ifdef HIPACC_B200_DEVICE_DSL
+template <size_t N, size_t A> struct alignas(A) Blob { unsigned char b[N]; };
+template <class K> __global__ void __launch_bounds__(kBlockX *kBlockY) dsl_kernel(const __grid_constant__ Blob<sizeof(K), alignof(K)> blob, int is_w, int is_h) {
+    if (gx() >= is_w || gy() >= is_h) return;
+    // the Kernel object as the host built it, references redirected to the device copies of what they point to.  It is
+    // used in place (constant bank): a body that ASSIGNS to a data member of its Kernel is not supported.
+    K &k = *const_cast<K *>(reinterpret_cast<const K *>(blob.b));
+    k.K::kernel();
+}
+
+// Launch dsl_kernel<K> for the host object `k`: every DSL object the Kernel refers to (its Accessor / Mask / Domain
+// reference members) is copied into a device arena together with the tables it owns, and the pointers inside the copy
+// of `k` are redirected to those copies.  `k` itself travels as the kernel parameter.
+template <class K> void launch_generic(K &k, const LaunchCtx &ctx) {
+    static_assert(sizeof(K) <= 3072, "Kernel object too large for the kernel parameter block");
+    Arena arena;
+    Blob<sizeof(K), alignof(K)> blob;
+    k.hb_fill_device_fields_(ctx.out_override);
+    std::memcpy(blob.b, (const void *)&k, sizeof(K));
+    struct Done { const void *host; size_t at; };
+    std::vector<Done> done;
+    std::vector<size_t> blob_fixups;   // byte offsets in blob.b holding (arena offset + 1)
+    const std::vector<Obj> objs = registry();
+    for (size_t off = 0; off + sizeof(void *) <= sizeof(K); off += sizeof(void *)) {
+        uintptr_t w;
+        std::memcpy(&w, blob.b + off, sizeof(w));
+        if (!w) continue;
+        for (const Obj &o : objs) {
+            const uintptr_t lo = (uintptr_t)o.host;
+            if (w < lo || w >= lo + o.size) continue;
+            size_t at = (size_t)-1;
+            for (const Done &d : done) if (d.host == o.host) at = d.at;
+            if (at == (size_t)-1) {
+                at = arena.put(o.host, o.size, 16);
+                done.push_back(Done{o.host, at});
+                o.prepare(o.host, at, arena);
+            }
+            const uintptr_t v = (uintptr_t)(at + (w - lo) + 1);
+            std::memcpy(blob.b + off, &v, sizeof(v));
+            blob_fixups.push_back(off);
+            break;
+        }
+    }
+    cudaStream_t s = (cudaStream_t)ctx.stream;
+    unsigned char *d_arena = nullptr;
+    auto ck = [](cudaError_t e, const char *what) {
+        if (e != cudaSuccess) std::fprintf(stderr, "ERROR: %s: %s\n", what, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    if (!arena.bytes.empty()) {
+        if (!ck(cudaMallocAsync((void **)&d_arena, arena.bytes.size(), s), "Kernel::execute() [compiled body]: cudaMallocAsync")) return;
+        for (size_t f : arena.fixups) {
+            uintptr_t v;
+            std::memcpy(&v, arena.bytes.data() + f, sizeof(v));
+            v = (uintptr_t)d_arena + (v - 1);
+            std::memcpy(arena.bytes.data() + f, &v, sizeof(v));
+        }
+        for (size_t f : blob_fixups) {
+            uintptr_t v;
+            std::memcpy(&v, blob.b + f, sizeof(v));
+            v = (uintptr_t)d_arena + (v - 1);
+            std::memcpy(blob.b + f, &v, sizeof(v));
+        }
+        ck(cudaMemcpyAsync(d_arena, arena.bytes.data(), arena.bytes.size(), cudaMemcpyHostToDevice, s), "Kernel::execute() [compiled body]: upload");
+    }
+    const int is_w = k.hb_is_width_(), is_h = k.hb_is_height_();
+    const dim3 block(kBlockX, kBlockY), grid((is_w + kBlockX - 1) / kBlockX, (is_h + kBlockY - 1) / kBlockY);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    const bool timed = hipacc_b200::timing_enabled() && cap == cudaStreamCaptureStatusNone;
+    if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+    dsl_kernel<K><<<grid, block, 0, s>>>(blob, is_w, is_h);
+    ck(cudaGetLastError(), "Kernel::execute() [compiled body]: launch");
+    if (timed) {
+        cudaEventRecord(e1, s);
+        ck(cudaEventSynchronize(e1), "Kernel::execute() [compiled body]");
+        cudaEventElapsedTime(&hipacc_b200::compiled_body_ms(), e0, e1);
+        hipacc_b200::compiled_body_was_last() = true;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (d_arena) cudaFreeAsync(d_arena, s);
+    if (ctx.launched) *ctx.launched = true;
+}
+#endif
+}}  // namespace b200::dev
+
 template <typename data_t, typename bin_t = data_t> class Kernel {
     IterationSpace<data_t> &iteration_space_;
     std::vector<AccessorBase *> inputs_;
     data_t reduction_result_{};
     bool executed_ = false, reduced_ = false;
+    // device-side fields of the compiled-body path (filled right before the object is copied into the launch)
+    data_t *d_out_ = nullptr;
+    int d_out_stride_ = 0, d_ox_ = 0, d_oy_ = 0;
 
     // identify the user's `reduce(left, right)` among {SUM, MIN, MAX, PROD} by evaluating it on probe values;
     // anything else has no device kernel
@@ -375,25 +735,82 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
         return -1;
     }
 
+    static bool check_requested() {
+        static int on = -1;
+        if (on < 0) { const char *e = std::getenv("HIPACC_B200_CHECK_LOWERING"); on = (e && std::atoi(e)) ? 1 : 0; }
+        return on == 1;
+    }
+    // HIPACC_B200_CHECK_LOWERING=1: run the compiled body into a scratch image and compare it with what lower() produced
+    void check_lowering(void *stream) {
+        const hb_view out = iteration_space_.rt().view();
+        hb_view scratch{};
+        hipacc_b200::check(hb_image_create(out.dtype, out.img_width, out.img_height, 0, &scratch), "check_lowering: scratch image");
+        if (scratch.stride != out.stride) {   // the body indexes with the iteration space's stride
+            std::fprintf(stderr, "hipacc_b200: HIPACC_B200_CHECK_LOWERING needs library-allocated images\n");
+            hb_image_destroy(&scratch);
+            return;
+        }
+        bool launched = false;
+        hb_dispatch_(b200::dev::LaunchCtx{stream, scratch.data, &launched});
+        if (!launched) {
+            std::fprintf(stderr, "hipacc_b200: HIPACC_B200_CHECK_LOWERING needs the translation unit compiled by nvcc (no device-compiled body here)\n");
+            hb_image_destroy(&scratch);
+            return;
+        }
+        std::vector<data_t> a((size_t)out.img_width * out.img_height), b(a.size());
+        hipacc_b200::check(hb_image_read(&out, a.data(), stream), "check_lowering: read");
+        hipacc_b200::check(hb_image_read(&scratch, b.data(), stream), "check_lowering: read");
+        hb_image_destroy(&scratch);
+        long bad = 0, first = -1;
+        for (int y = 0; y < out.height; ++y)
+            for (int x = 0; x < out.width; ++x) {
+                const size_t i = (size_t)(y + out.offset_y) * out.img_width + x + out.offset_x;
+                if (!b200::pixels_agree(a[i], b[i])) { if (!bad) first = (long)i; ++bad; }
+            }
+        if (bad) {
+            std::fprintf(stderr, "hipacc_b200: lower() and kernel() DISAGREE on %ld of %ld pixels (first at index %ld): the lowering does not "
+                                 "describe this body\n", bad, (long)out.width * out.height, first);
+            std::abort();
+        }
+    }
+
   public:
     explicit Kernel(IterationSpace<data_t> &iteration_space) : iteration_space_(iteration_space) {}
     virtual ~Kernel() = default;
-    virtual void kernel() = 0;
+    HB_HD virtual void kernel() = 0;
     virtual b200::Lowering lower() { return {}; }
     virtual bin_t reduce(bin_t, bin_t) const { assert(false && "No reduce method specified"); return {}; }
     virtual void binning(unsigned int, unsigned int, data_t) { assert(false && "No binning method specified"); }  // dsl/kernel.hpp:91
     virtual b200::Binning lower_binning() { return {}; }
     void add_accessor(AccessorBase *acc) { inputs_.push_back(acc); }
 
-    void execute(const HipaccExecutionParameterCuda &ep = nullptr) {
+    // the typed launch hook of the compiled-body path: the macro at the end of this header overrides it in every Kernel
+    // subclass that an nvcc-compiled translation unit defines.  false = this class has no device-compiled body.
+    virtual void hb_dispatch_(const b200::dev::LaunchCtx &c) { if (c.launched) *c.launched = false; }
+    void hb_fill_device_fields_(void *out_override) {
+        const hb_view v = iteration_space_.rt().view();
+        d_out_ = static_cast<data_t *>(out_override ? out_override : v.data);
+        d_out_stride_ = v.stride; d_ox_ = v.offset_x; d_oy_ = v.offset_y;
+    }
+    int hb_is_width_() const { return iteration_space_.width(); }
+    int hb_is_height_() const { return iteration_space_.height(); }
+
+    template <typename T_EP> void execute(T_EP &&ep) { execute_on(ep); }
+    void execute() { execute_on(nullptr); }
+    void execute_on(const HipaccExecutionParameterCuda &ep) {
         if (executed_) return;  // idempotent per Kernel object (dsl/kernel.hpp:95,117)
+        void *stream = ep ? ep->get_stream() : nullptr;
         b200::Lowering L = lower();
-        if (L.kind == b200::Lowering::NONE || !L.launch) {
-            std::fprintf(stderr, "ERROR: Kernel::execute(): this Kernel has no lower(); there is no host fallback\n");
+        if (ep) ep->pre_kernel();
+        if (L.kind != b200::Lowering::NONE && L.launch) {
+            hipacc_b200::compiled_body_was_last() = false;
+            L.launch(iteration_space_.rt().view(), stream);
+            if (check_requested()) check_lowering(stream);
+        } else if (bool launched = false; hb_dispatch_(b200::dev::LaunchCtx{stream, nullptr, &launched}), !launched) {
+            std::fprintf(stderr, "ERROR: Kernel::execute(): this Kernel has neither a lower() nor a device-compiled kernel() body "
+                                 "(compile the translation unit with nvcc); there is no host fallback\n");
             return;
         }
-        if (ep) ep->pre_kernel();
-        L.launch(iteration_space_.rt().view(), ep ? ep->get_stream() : nullptr);
         if (ep) ep->post_kernel();
         executed_ = true;
     }
@@ -430,13 +847,92 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
     unsigned int num_bins_ = 0;
     unsigned int num_bins() const { return num_bins_; }
     bin_t &bin(const unsigned int) { b200::host_body_called(); }
-    // kernel()-body vocabulary; compiles, never runs on the host
-    data_t &output() { b200::host_body_called(); }
-    int x() const { b200::host_body_called(); }
-    int y() const { b200::host_body_called(); }
-    template <typename M, typename F> auto convolve(M &, Reduce, const F &f) -> decltype(f()) { b200::host_body_called(); }
-    template <typename F> auto reduce(Domain &, Reduce, const F &f) -> decltype(f()) { b200::host_body_called(); }
-    template <typename F> void iterate(Domain &, const F &) { b200::host_body_called(); }
+
+    // ---- kernel()-body vocabulary: device code under nvcc, never run on the host -------------------------------------
+    HB_HD data_t &output() {
+#ifdef __CUDA_ARCH__
+        return d_out_[(size_t)(d_oy_ + b200::dev::gy()) * d_out_stride_ + d_ox_ + b200::dev::gx()];
+#else
+        b200::host_body_called();
+#endif
+    }
+    // x and y refer to the area defined by the iteration space (dsl/kernel.hpp:131-133)
+    HB_HD data_t &output_at(const int xf, const int yf) {
+#ifdef __CUDA_ARCH__
+        return d_out_[(size_t)(d_oy_ + yf) * d_out_stride_ + d_ox_ + xf];
+#else
+        (void)xf; (void)yf; b200::host_body_called();
+#endif
+    }
+    HB_HD int x() const {
+#ifdef __CUDA_ARCH__
+        return b200::dev::gx();
+#else
+        b200::host_body_called();
+#endif
+    }
+    HB_HD int y() const {
+#ifdef __CUDA_ARCH__
+        return b200::dev::gy();
+#else
+        b200::host_body_called();
+#endif
+    }
+    // dsl/kernel.hpp:241-267: row-major over the mask, the first tap initialises, every later one folds by `mode`
+    template <typename data_m, typename F> HB_HD auto convolve(Mask<data_m> &mask, Reduce mode, const F &fun) -> decltype(fun()) {
+#ifdef __CUDA_ARCH__
+        const int sx = mask.size_x(), sy = mask.size_y();
+        mask.dev_seek(-(sx / 2), -(sy / 2));
+        auto result = fun();
+        for (int k = 1; k < sx * sy; ++k) {
+            mask.dev_seek(k % sx - sx / 2, k / sx - sy / 2);
+            fold_(result, fun(), mode);
+        }
+        return result;
+#else
+        (void)mask; (void)mode; (void)fun; b200::host_body_called();
+#endif
+    }
+    // dsl/kernel.hpp:270-296 with the Domain's holes skipped (dsl/mask.hpp:112-126)
+    template <typename F> HB_HD auto reduce(Domain &dom, Reduce mode, const F &fun) -> decltype(fun()) {
+#ifdef __CUDA_ARCH__
+        const int sx = dom.size_x(), sy = dom.size_y();
+        decltype(fun()) result{};
+        bool first = true;
+        for (int k = 0; k < sx * sy; ++k) {
+            if (!dom.dev_visited(k)) continue;
+            dom.dev_seek(k % sx - sx / 2, k / sx - sy / 2);
+            if (first) { result = fun(); first = false; }
+            else fold_(result, fun(), mode);
+        }
+        return result;
+#else
+        (void)dom; (void)mode; (void)fun; b200::host_body_called();
+#endif
+    }
+    template <typename F> HB_HD void iterate(Domain &dom, const F &fun) {
+#ifdef __CUDA_ARCH__
+        const int sx = dom.size_x(), sy = dom.size_y();
+        for (int k = 0; k < sx * sy; ++k) {
+            if (!dom.dev_visited(k)) continue;
+            dom.dev_seek(k % sx - sx / 2, k / sx - sy / 2);
+            fun();
+        }
+#else
+        (void)dom; (void)fun; b200::host_body_called();
+#endif
+    }
+
+  private:
+    template <typename R> HB_HD static void fold_(R &result, const R &v, Reduce mode) {
+        switch (mode) {
+        case Reduce::SUM: result += v; break;
+        case Reduce::MIN: result = hipacc::math::min(v, result); break;
+        case Reduce::MAX: result = hipacc::math::max(v, result); break;
+        case Reduce::PROD: result *= v; break;
+        default: break;
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -474,5 +970,19 @@ inline void traverse(std::vector<PyramidBase *> const &pyrs, const std::function
 inline void traverse(int loop = 1, const std::function<void()> &f = [] {}) { hipaccTraverse((unsigned)loop, f); }
 
 }  // namespace hipacc
+
+// ---------------------------------------------------------------------------------------------------
+// The compiled-body hook.  Under nvcc every `void kernel() { ... }` a Kernel subclass defines after this point becomes
+//     void hb_dispatch_(ctx) override { launch dsl_kernel<ThisClass> }        <- typed launch of this very class
+//     __host__ __device__ void kernel() { ... }                               <- the body, now device code
+// so that sample sources compile unmodified (dsl/kernel.hpp:79 declares `virtual void kernel() = 0`).
+// ---------------------------------------------------------------------------------------------------
+#ifdef HIPACC_B200_DEVICE_DSL
+#define kernel()                                                                       \
+    hb_dispatch_(const ::hipacc::b200::dev::LaunchCtx &hb_ctx_) override {             \
+        ::hipacc::b200::dev::launch_generic(*this, hb_ctx_);                           \
+    }                                                                                  \
+    __host__ __device__ void kernel()
+#endif
 
 #endif  // HIPACC_B200_DSL_HPP

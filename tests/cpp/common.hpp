@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace tc {
@@ -73,6 +74,31 @@ inline int verdict(const char *name, long bad, size_t n, long first) {
     }
     std::printf("%s: Test FAILED, %ld of %zu pixels differ (first at index %ld)\n", name, bad, n, first);
     return 1;
+}
+
+// command line of the compiled-body programs: [width height] [--io in.raw out.raw] (raw = dense pixels, row-major); the
+// GPU tests feed the inputs of tests/golden/*.npz through --io and compare the output file with the golden array
+struct Args {
+    int w, h;
+    const char *in = nullptr, *out = nullptr;
+    Args(int argc, char **argv, int w0, int h0) : w(w0), h(h0) {
+        int pos = 0;
+        for (int i = 1; i < argc; ++i) {
+            if (!std::strcmp(argv[i], "--io") && i + 2 < argc) { in = argv[i + 1]; out = argv[i + 2]; i += 2; }
+            else if (pos == 0) { w = std::atoi(argv[i]); ++pos; }
+            else if (pos == 1) { h = std::atoi(argv[i]); ++pos; }
+        }
+    }
+};
+template <typename T> inline void read_raw(const char *path, std::vector<T> &v) {
+    std::FILE *f = std::fopen(path, "rb");
+    if (!f || std::fread(v.data(), sizeof(T), v.size(), f) != v.size()) { std::fprintf(stderr, "cannot read %s\n", path); std::exit(2); }
+    std::fclose(f);
+}
+template <typename T> inline void write_raw(const char *path, const T *p, size_t n) {
+    std::FILE *f = std::fopen(path, "wb");
+    if (!f || std::fwrite(p, sizeof(T), n, f) != n) { std::fprintf(stderr, "cannot write %s\n", path); std::exit(2); }
+    std::fclose(f);
 }
 
 }  // namespace tc
