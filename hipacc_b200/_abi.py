@@ -17,7 +17,7 @@ NUMPY_DTYPE = {v: k for k, v in DTYPE_NUMPY.items()}
 UNDEFINED, CLAMP, REPEAT, MIRROR, CONSTANT = range(5)
 BOUNDARY_NAMES = {UNDEFINED: "UNDEFINED", CLAMP: "CLAMP", REPEAT: "REPEAT", MIRROR: "MIRROR", CONSTANT: "CONSTANT"}
 # hb_interp == hipacc::Interpolate (dsl/image.hpp:54-61)
-INTERP_NO, INTERP_NN, INTERP_LF = range(3)
+INTERP_NO, INTERP_NN, INTERP_LF, INTERP_B5, INTERP_CF, INTERP_L3 = range(6)
 # hb_reduce_mode == hipacc::Reduce (dsl/kernel.hpp:48-54)
 SUM, MIN, MAX, PROD = range(4)
 # hb_local_kind / hb_tap / hb_epilogue

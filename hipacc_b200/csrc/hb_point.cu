@@ -33,7 +33,53 @@ struct PointParams {
     int pi[2];
 };
 
-// accessor value for output pixel (gx,gy) through NN / LF interpolation (dsl/image.hpp:390-422)
+// ---- B5 / CF / L3 (dsl/image.hpp:321-528): TAPS x TAPS neighbourhood, weights from the fractional position --------------
+__device__ __forceinline__ float w_binomial5(float d) {
+    d = fabsf(d);
+    return d < 0.5f ? 0.75f : d < 1.0f ? 0.5f : d < 1.5f ? 0.125f : 0.0f;
+}
+__device__ __forceinline__ float w_bicubic(float d) {   // Keys, a = -0.5; the library is built with -fmad=false: every * and + rounds
+    d = fabsf(d);
+    const float a = -0.5f;
+    if (d < 1.0f) return (a + 2.0f) * d * d * d - (a + 3.0f) * d * d + 1.0f;
+    if (d < 2.0f) return a * d * d * d - 5.0f * a * d * d + 8.0f * a * d - 4.0f * a;
+    return 0.0f;
+}
+__device__ __forceinline__ float w_lanczos3(float d) {   // the reference evaluates this in double and rounds once
+    d = fabsf(d);
+    const double pi = 3.14159265358979323846;   // == atan(1.0) * 4 in double
+    if (d == 0.0f) return 1.0f;
+    if (d < 3.0f) return (float)(3.0 * (sin(pi * (double)d / 3.0) * sin(pi * (double)d)) / (pi * pi * (double)d * (double)d));
+    return 0.0f;
+}
+template <typename T, int MODE>
+__device__ __forceinline__ T fetch_interp_wide(const ImgRef<T> &im, const Window &w, int x_int, int y_int, float fx, float fy) {
+    constexpr int TAPS = MODE == HB_INTERP_L3 ? 6 : 4;
+    constexpr int X0 = MODE == HB_INTERP_B5 ? 0 : MODE == HB_INTERP_CF ? -1 : -2;
+    constexpr int Y0 = MODE == HB_INTERP_B5 ? 0 : -1;   // L3's rows start at y_int - 1 (dsl/image.hpp:478), kept
+    if (MODE == HB_INTERP_B5) { fx = (float)((double)fx + 0.5); fy = (float)((double)fy + 0.5); }
+    float wx[TAPS];
+#pragma unroll
+    for (int i = 0; i < TAPS; ++i)
+        wx[i] = MODE == HB_INTERP_B5 ? w_binomial5(fx - i) : MODE == HB_INTERP_CF ? w_bicubic(fx - 1 + i) : w_lanczos3(fx - 2 + i);
+    float r = 0.0f;
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < TAPS; ++i) {
+            // the reference's second Lanczos row repeats the weight of tap 5 for tap 4 (dsl/image.hpp:489): kept, it decides results
+            const float wgt = (MODE == HB_INTERP_L3 && j == 1 && i == 4) ? wx[5] : wx[i];
+            const float v = (float)fetch_bh(im, w, x_int + X0 + i, y_int + Y0 + j, T(0)) * wgt;
+            acc = i == 0 ? v : acc + v;
+        }
+        const float wy = MODE == HB_INTERP_B5 ? w_binomial5(fy - j) : MODE == HB_INTERP_CF ? w_bicubic(fy - 1 + j) : w_lanczos3(fy - 2 + j);
+        r = j == 0 ? acc * wy : r + acc * wy;
+    }
+    return cast_out<T, float>(r);
+}
+
+// accessor value for output pixel (gx,gy) through the accessor's interpolation mode (dsl/image.hpp:390-528)
 template <typename T>
 __device__ __forceinline__ T fetch_interp(const PointIn &a, int gx, int gy, int is_w, int is_h) {
     ImgRef<T> im{static_cast<const T *>(a.p), a.stride, a.iw, a.ih};
@@ -50,6 +96,9 @@ __device__ __forceinline__ T fetch_interp(const PointIn &a, int gx, int gy, int 
     if (yb < 0.0f) yb = 0.0f;
     const int x_int = __float2int_rz(xb), y_int = __float2int_rz(yb);
     const float xf = __fadd_rn(xb, -(float)x_int), yf = __fadd_rn(yb, -(float)y_int);
+    if (a.interp == HB_INTERP_B5) return fetch_interp_wide<T, HB_INTERP_B5>(im, w, x_int, y_int, xf, yf);
+    if (a.interp == HB_INTERP_CF) return fetch_interp_wide<T, HB_INTERP_CF>(im, w, x_int, y_int, xf, yf);
+    if (a.interp == HB_INTERP_L3) return fetch_interp_wide<T, HB_INTERP_L3>(im, w, x_int, y_int, xf, yf);
     const float omx = __fadd_rn(1.0f, -xf), omy = __fadd_rn(1.0f, -yf);
     const float p00 = (float)fetch_bh(im, w, x_int, y_int, T(0));
     const float p10 = (float)fetch_bh(im, w, x_int + 1, y_int, T(0));
@@ -229,7 +278,7 @@ extern "C" int hb_point_op(const hb_point_desc *d, void *stream) {
         }
         HB_REQUIRE(view_ok(v) && v.dtype == it, HB_ERR_INVALID, "hb_point_op: malformed input view %d (all inputs share one pixel type)", k);
         const int ip = d->interp[k];
-        HB_REQUIRE(ip >= HB_INTERP_NO && ip <= HB_INTERP_LF, HB_ERR_UNSUPPORTED, "hb_point_op: interpolation mode %d not implemented", ip);
+        HB_REQUIRE(ip >= HB_INTERP_NO && ip <= HB_INTERP_L3, HB_ERR_INVALID, "hb_point_op: unknown interpolation mode %d", ip);
         HB_REQUIRE(ip != HB_INTERP_NO || (v.width >= out.width && v.height >= out.height), HB_ERR_INVALID,
                    "hb_point_op: input %d region smaller than the iteration space", k);
         p.in[k] = PointIn{v.data, v.stride, v.img_width, v.img_height, v.width, v.height, v.offset_x, v.offset_y, ip};

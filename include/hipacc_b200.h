@@ -55,8 +55,9 @@ typedef enum {  /* hipacc::Boundary, dsl/image.hpp:46-52 */
   HB_BOUNDARY_MIRROR = 3, HB_BOUNDARY_CONSTANT = 4
 } hb_boundary;
 
-typedef enum {  /* hipacc::Interpolate, dsl/image.hpp:54-61 (NO, NN, LF implemented) */
-  HB_INTERP_NO = 0, HB_INTERP_NN = 1, HB_INTERP_LF = 2
+typedef enum {  /* hipacc::Interpolate, dsl/image.hpp:54-61: nearest neighbour, bilinear, binomial 5 (4 x 4 taps), bicubic
+                 * convolution (4 x 4), Lanczos 3 (6 x 6) */
+  HB_INTERP_NO = 0, HB_INTERP_NN = 1, HB_INTERP_LF = 2, HB_INTERP_B5 = 3, HB_INTERP_CF = 4, HB_INTERP_L3 = 5
 } hb_interp;
 
 typedef enum {  /* hipacc::Reduce, dsl/kernel.hpp:48-54 */

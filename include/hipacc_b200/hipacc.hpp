@@ -87,6 +87,41 @@ __device__ __forceinline__ int &iter_state(int slot) {
 }
 #endif
 
+#ifdef __CUDACC__
+constexpr int kInterpSlots = 4;    // interpolating Accessors one kernel() body may read
+// size of the iteration space (the interpolating accessors scale by it), published by every thread of the CTA
+__device__ __forceinline__ int *is_dims() {
+    __shared__ int dims[2];
+    return dims;
+}
+// an interpolating accessor returns a reference to a computed value (dsl/image.hpp:310-318 keeps it in the Accessor): one
+// 16-byte cell per (accessor, thread)
+template <typename T> __device__ __forceinline__ T &interp_cell(int slot) {
+    static_assert(sizeof(T) <= 16, "pixel type too large");
+    __shared__ __align__(16) unsigned char cells[kInterpSlots][kBlockX * kBlockY][16];
+    return *reinterpret_cast<T *>(cells[slot][threadIdx.y * kBlockX + threadIdx.x]);
+}
+#endif
+// interpolation weights (dsl/image.hpp:321-383)
+HB_HD float w_binomial5(float d) {
+    d = d < 0 ? -d : d;
+    return d < 0.5f ? 6.0f / 8.0f : d < 1.0f ? 4.0f / 8.0f : d < 1.5f ? 1.0f / 8.0f : 0.0f;
+}
+HB_HD float w_bicubic(float d) {   // Keys' cubic convolution, a = -0.5
+    d = d < 0 ? -d : d;
+    const float a = -0.5f;
+    if (d < 1.0f) return (a + 2.0f) * d * d * d - (a + 3.0f) * d * d + 1.0f;
+    if (d < 2.0f) return a * d * d * d - 5.0f * a * d * d + 8.0f * a * d - 4.0f * a;
+    return 0.0f;
+}
+HB_HD float w_lanczos3(float d) {   // evaluated in double, rounded once
+    d = d < 0 ? -d : d;
+    const double pi = 3.14159265358979323846;
+    if (d == 0.0f) return 1.0f;
+    if (d < 3.0f) return (float)(3.0 * (sin(pi * (double)d / 3.0) * sin(pi * (double)d)) / (pi * pi * (double)d * (double)d));
+    return 0.0f;
+}
+
 // index remapping of a boundary mode on [lo, hi) (dsl/image.hpp:574-612; decisions of SURVEY.md 8c: REPEAT wraps with
 // `while`, upper test first) -- the same function the library's tile loaders apply (csrc/hb_common.cuh)
 HB_HD int remap(int idx, int lo, int hi, Boundary mode) {
@@ -130,7 +165,7 @@ inline void retire(const void *p) {
 struct Arena {
     std::vector<unsigned char> bytes;
     std::vector<size_t> fixups;   // offsets (within bytes) of pointer fields holding (arena offset + 1)
-    int next_slot = 0;
+    int next_slot = 0, next_interp_slot = 0;
     size_t put(const void *src, size_t n, size_t align = 16) {
         const size_t at = (bytes.size() + align - 1) / align * align;
         bytes.resize(at + n);
@@ -345,7 +380,7 @@ class AccessorBase {
 template <typename data_t> class Accessor : public AccessorBase {
     // device-side fields, valid in the snapshot a launch makes
     data_t *d_ptr_ = nullptr;
-    int d_stride_ = 0, d_iw_ = 0, d_ih_ = 0;
+    int d_stride_ = 0, d_iw_ = 0, d_ih_ = 0, d_islot_ = 0;
     data_t d_const_{};
 
     static void prepare(const void *host_obj, size_t snap_at, b200::dev::Arena &arena) {
@@ -355,6 +390,13 @@ template <typename data_t> class Accessor : public AccessorBase {
         snap.d_ptr_ = static_cast<data_t *>(v.data);
         snap.d_stride_ = v.stride; snap.d_iw_ = v.img_width; snap.d_ih_ = v.img_height;
         snap.d_const_ = a.const_val;
+        if (a.imode != Interpolate::NO) {
+            snap.d_islot_ = arena.next_interp_slot++;
+            if (snap.d_islot_ >= 4) {
+                std::fprintf(stderr, "hipacc_b200: a kernel() body may read at most 4 interpolating Accessors\n");
+                std::abort();
+            }
+        }
     }
 
   public:
@@ -401,9 +443,8 @@ template <typename data_t> class Accessor : public AccessorBase {
     }
 
 #ifdef __CUDA_ARCH__
-    // pixel (IS-relative position + offset) through the boundary mode of this accessor's region
-    __device__ __forceinline__ data_t &dev_fetch(int dx, int dy) const {
-        int x = offset_x_ + b200::dev::gx() + dx, y = offset_y_ + b200::dev::gy() + dy;
+    // image pixel (x, y) through the boundary mode of this accessor's region: pixel_bh of dsl/image.hpp:574-612
+    __device__ __forceinline__ data_t &dev_pixel_bh(int x, int y) const {
         if (bmode == Boundary::CONSTANT) {
             if (x < offset_x_ || x >= offset_x_ + width_ || y < offset_y_ || y >= offset_y_ + height_) return const_cast<data_t &>(d_const_);
         } else if (bmode != Boundary::UNDEFINED) {
@@ -414,8 +455,50 @@ template <typename data_t> class Accessor : public AccessorBase {
         y = y < 0 ? 0 : y >= d_ih_ ? d_ih_ - 1 : y;
         return d_ptr_[(size_t)y * d_stride_ + x];
     }
+    // the value this thread's pixel sees at tap (dx, dy): plain, or through the interpolation mode (dsl/image.hpp:390-528)
+    __device__ __forceinline__ data_t &dev_fetch(int dx, int dy) const {
+        using hipacc_b200::to_float;
+        typedef typename hipacc_b200::float_of<data_t>::type F;
+        if (imode == Interpolate::NO) return dev_pixel_bh(offset_x_ + b200::dev::gx() + dx, offset_y_ + b200::dev::gy() + dy);
+        const int *is = b200::dev::is_dims();
+        const float stride_x = width_ / (float)is[0], stride_y = height_ / (float)is[1];
+        const float x_mapped = offset_x_ + stride_x / 2 + stride_x * (b200::dev::gx() + dx);
+        const float y_mapped = offset_y_ + stride_y / 2 + stride_y * (b200::dev::gy() + dy);
+        data_t &cell = b200::dev::interp_cell<data_t>(d_islot_);
+        if (imode == Interpolate::NN) { cell = dev_pixel_bh((int)x_mapped, (int)y_mapped); return cell; }
+        float xb = x_mapped - 0.5f, yb = y_mapped - 0.5f;
+        if (xb < 0.0f) xb = 0.0f;
+        if (yb < 0.0f) yb = 0.0f;
+        const int xi = (int)xb, yi = (int)yb;
+        float fx = xb - xi, fy = yb - yi;
+        if (imode == Interpolate::LF) {
+            const F r = (1.0f - fx) * (1.0f - fy) * to_float(dev_pixel_bh(xi, yi)) + fx * (1.0f - fy) * to_float(dev_pixel_bh(xi + 1, yi)) +
+                        (1.0f - fx) * fy * to_float(dev_pixel_bh(xi, yi + 1)) + fx * fy * to_float(dev_pixel_bh(xi + 1, yi + 1));
+            cell = hipacc_b200::from_float<data_t>(r);
+            return cell;
+        }
+        // B5 / CF / L3: TAPS x TAPS neighbourhood; L3's rows start at y - 1 and its second row repeats the weight of tap 5
+        // (dsl/image.hpp:478,489) -- kept, they decide results
+        const bool b5 = imode == Interpolate::B5, cf = imode == Interpolate::CF;
+        const int taps = (b5 || cf) ? 4 : 6, x0 = b5 ? 0 : cf ? -1 : -2, y0 = b5 ? 0 : -1;
+        if (b5) { fx = (float)((double)fx + 0.5); fy = (float)((double)fy + 0.5); }
+        F r{};
+        for (int j = 0; j < taps; ++j) {
+            F acc{};
+            for (int i = 0; i < taps; ++i) {
+                const int wi = (!b5 && !cf && j == 1 && i == 4) ? 5 : i;
+                const float w = b5 ? b200::dev::w_binomial5(fx - wi) : cf ? b200::dev::w_bicubic(fx - 1 + wi) : b200::dev::w_lanczos3(fx - 2 + wi);
+                const F v = to_float(dev_pixel_bh(xi + x0 + i, yi + y0 + j)) * w;
+                if (i == 0) acc = v; else acc = acc + v;
+            }
+            const float wy = b5 ? b200::dev::w_binomial5(fy - j) : cf ? b200::dev::w_bicubic(fy - 1 + j) : b200::dev::w_lanczos3(fy - 2 + j);
+            if (j == 0) r = acc * wy; else r = r + acc * wy;
+        }
+        cell = hipacc_b200::from_float<data_t>(r);
+        return cell;
+    }
 #endif
-    // kernel()-body forms (interpolating accessors are served by the lowered point operators only)
+    // kernel()-body forms
     HB_HD data_t &operator()() {
 #ifdef __CUDA_ARCH__
         return dev_fetch(0, 0);
@@ -445,16 +528,16 @@ template <typename data_t> class Accessor : public AccessorBase {
         (void)x; (void)y; b200::host_body_called();
 #endif
     }
-    HB_HD int x() const {
+    HB_HD int x() const {   // dsl/image.hpp:692-698
 #ifdef __CUDA_ARCH__
-        return b200::dev::gx();
+        return imode == Interpolate::NO ? b200::dev::gx() : (int)(b200::dev::gx() * width_ / (float)b200::dev::is_dims()[0]);
 #else
         b200::host_body_called();
 #endif
     }
     HB_HD int y() const {
 #ifdef __CUDA_ARCH__
-        return b200::dev::gy();
+        return imode == Interpolate::NO ? b200::dev::gy() : (int)(b200::dev::gy() * height_ / (float)b200::dev::is_dims()[1]);
 #else
         b200::host_body_called();
 #endif
@@ -626,10 +709,12 @@ inline Lowering harris(const Accessor<uchar> &in, float k, float threshold) {
 // ---------------------------------------------------------------------------------------------------
 // Kernel (dsl/kernel.hpp:56-330)
 // ---------------------------------------------------------------------------------------------------
+template <typename data_t, typename bin_t = data_t> class Kernel;
 namespace b200 { namespace dev {
 #ifdef HIPACC_B200_DEVICE_DSL
 template <size_t N, size_t A> struct alignas(A) Blob { unsigned char b[N]; };
 template <class K> __global__ void __launch_bounds__(kBlockX *kBlockY) dsl_kernel(const __grid_constant__ Blob<sizeof(K), alignof(K)> blob, int is_w, int is_h) {
+    is_dims()[0] = is_w; is_dims()[1] = is_h;   // every thread writes the same two values
     if (gx() >= is_w || gy() >= is_h) return;
     // the Kernel object as the host built it, references redirected to the device copies of what they point to.  It is
     // used in place (constant bank): a body that ASSIGNS to a data member of its Kernel is not supported.
@@ -711,10 +796,137 @@ template <class K> void launch_generic(K &k, const LaunchCtx &ctx) {
     if (d_arena) cudaFreeAsync(d_arena, s);
     if (ctx.launched) *ctx.launched = true;
 }
+
+// ---- compiled reduce() / binning() bodies (dsl/kernel.hpp:121-199) over the OUTPUT image of the iteration space -----------
+template <class K> struct kernel_types;   // data_t / bin_t of a Kernel subclass
+template <class D, class B> D data_type_of(const Kernel<D, B> *);
+template <class D, class B> B bin_type_of(const Kernel<D, B> *);
+
+// one partial per CTA: tree fold of the CTA's pixels with K::reduce; the host folds the partials in CTA order
+template <class K, class D> __global__ void __launch_bounds__(kBlockX *kBlockY) dsl_reduce_kernel(const __grid_constant__ Blob<sizeof(K), alignof(K)> blob,
+                                                                                                 int is_w, int is_h, D *partials) {
+    __shared__ __align__(16) unsigned char raw[kBlockX * kBlockY * sizeof(D)];
+    __shared__ unsigned char valid[kBlockX * kBlockY];
+    D *vals = reinterpret_cast<D *>(raw);
+    const K &k = *reinterpret_cast<const K *>(blob.b);
+    const int tid = threadIdx.y * kBlockX + threadIdx.x;
+    const bool in = gx() < is_w && gy() < is_h;
+    valid[tid] = in;
+    if (in) vals[tid] = const_cast<K &>(k).hb_output_();
+    __syncthreads();
+    for (int stride = kBlockX * kBlockY / 2; stride > 0; stride >>= 1) {
+        if (tid < stride && valid[tid + stride]) {
+            vals[tid] = valid[tid] ? k.K::reduce(vals[tid], vals[tid + stride]) : vals[tid + stride];
+            valid[tid] = 1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = vals[0];
+}
+
+// bins[idx] = reduce(bins[idx], value) for every pixel's `bin(idx) = value`.  reduce() is arbitrary code, not an atomic
+// instruction, so a bin is updated by a compare-and-swap loop on its bit pattern (4- and 8-byte bins; no locks, nothing can
+// dead-lock).  Each CTA folds into a private copy of the bins in shared memory first (when they fit) and merges the bins it
+// touched into the global ones at the end.  As in the reference's GPU runtime (runtime/hipacc_cu_red.hpp:527-641) reduce()
+// must be associative and commutative and must accept bin_t() as the start value of every partial fold.
+template <class B> struct bin_word { typedef typename std::conditional<sizeof(B) == 8, unsigned long long, unsigned int>::type type; };
+template <class K, class B> __device__ __forceinline__ void bin_update(const K &k, B *slot, const B &val) {
+    typedef typename bin_word<B>::type W;
+    W *w = reinterpret_cast<W *>(slot);
+    W old = *reinterpret_cast<volatile W *>(w), assumed;
+    do {
+        assumed = old;
+        B cur;
+        memcpy(&cur, &assumed, sizeof(B));
+        const B next = k.K::reduce(cur, val);
+        W nw;
+        memcpy(&nw, &next, sizeof(B));
+        old = atomicCAS(w, assumed, nw);
+    } while (old != assumed);
+}
+template <class K, class B> __global__ void __launch_bounds__(kBlockX *kBlockY) dsl_binning_kernel(const __grid_constant__ Blob<sizeof(K), alignof(K)> blob,
+                                                                                                  int is_w, int is_h, unsigned int num_bins, B *bins,
+                                                                                                  int private_bins) {
+    extern __shared__ __align__(16) unsigned char hb_bins_raw[];
+    B *sbins = reinterpret_cast<B *>(hb_bins_raw);
+    const int tid = threadIdx.y * kBlockX + threadIdx.x;
+    is_dims()[0] = is_w; is_dims()[1] = is_h;
+    if (private_bins) {
+        for (unsigned int b = tid; b < num_bins; b += kBlockX * kBlockY) sbins[b] = B();
+        __syncthreads();
+    }
+    alignas(K) unsigned char local[sizeof(K)];   // binning() stores into the Kernel object: each thread works on its own copy
+    memcpy(local, blob.b, sizeof(K));
+    K &k = *reinterpret_cast<K *>(local);
+    if (gx() < is_w && gy() < is_h) {
+        k.K::binning((unsigned int)gx(), (unsigned int)gy(), k.hb_output_());
+        const unsigned int idx = k.hb_bin_idx_();
+        if (idx < num_bins) bin_update<K, B>(k, (private_bins ? sbins : bins) + idx, k.hb_bin_val_());   // out of range: the reference asserts
+    }
+    if (private_bins) {
+        __syncthreads();
+        typedef typename bin_word<B>::type W;
+        const B zero = B();
+        W zw;
+        memcpy(&zw, &zero, sizeof(B));
+        for (unsigned int b = tid; b < num_bins; b += kBlockX * kBlockY)
+            if (reinterpret_cast<const W *>(sbins)[b] != zw) bin_update<K, B>(k, bins + b, sbins[b]);
+    }
+}
+
+template <class K> void launch_global(K &k, const LaunchCtx &ctx, int what, unsigned int num_bins, void *result) {
+    typedef decltype(data_type_of(&k)) D;
+    typedef decltype(bin_type_of(&k)) B;
+    Blob<sizeof(K), alignof(K)> blob;
+    k.hb_fill_device_fields_(nullptr);
+    std::memcpy(blob.b, (const void *)&k, sizeof(K));   // reduce() / binning() see the Kernel's scalar members; no Accessor is read
+    const int is_w = k.hb_is_width_(), is_h = k.hb_is_height_();
+    const dim3 block(kBlockX, kBlockY), grid((is_w + kBlockX - 1) / kBlockX, (is_h + kBlockY - 1) / kBlockY);
+    cudaStream_t s = (cudaStream_t)ctx.stream;
+    auto ck = [](cudaError_t e, const char *what_) {
+        if (e != cudaSuccess) std::fprintf(stderr, "ERROR: %s: %s\n", what_, cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    if (what == 0) {
+        if constexpr (std::is_same<D, B>::value) {
+            const size_t n = (size_t)grid.x * grid.y;
+            D *d_part = nullptr;
+            if (!ck(cudaMalloc((void **)&d_part, n * sizeof(D)), "Kernel::reduced_data() [compiled body]")) return;
+            dsl_reduce_kernel<K, D><<<grid, block, 0, s>>>(blob, is_w, is_h, d_part);
+            std::vector<D> part(n);
+            ck(cudaMemcpyAsync(part.data(), d_part, n * sizeof(D), cudaMemcpyDeviceToHost, s), "Kernel::reduced_data() [compiled body]");
+            ck(cudaStreamSynchronize(s), "Kernel::reduced_data() [compiled body]");
+            cudaFree(d_part);
+            D r = part[0];
+            for (size_t i = 1; i < n; ++i) r = k.K::reduce(r, part[i]);
+            *static_cast<D *>(result) = r;
+        } else {
+            std::fprintf(stderr, "ERROR: Kernel::reduced_data(): reduce() works on bin_t, which differs from the pixel type\n");
+            return;
+        }
+    } else {
+        if constexpr (sizeof(B) == 4 || sizeof(B) == 8) {
+            B *d_bins = nullptr;
+            if (!ck(cudaMalloc((void **)&d_bins, num_bins * sizeof(B)), "Kernel::binned_data() [compiled body]")) return;
+            ck(cudaMemcpyAsync(d_bins, result, num_bins * sizeof(B), cudaMemcpyHostToDevice, s), "Kernel::binned_data() [compiled body]");   // bin_t() each
+            const size_t smem = (size_t)num_bins * sizeof(B);
+            const int priv = smem <= 32 * 1024;
+            dsl_binning_kernel<K, B><<<grid, block, priv ? smem : 0, s>>>(blob, is_w, is_h, num_bins, d_bins, priv);
+            ck(cudaGetLastError(), "Kernel::binned_data() [compiled body]: launch");
+            ck(cudaMemcpyAsync(result, d_bins, num_bins * sizeof(B), cudaMemcpyDeviceToHost, s), "Kernel::binned_data() [compiled body]");
+            ck(cudaStreamSynchronize(s), "Kernel::binned_data() [compiled body]");
+            cudaFree(d_bins);
+        } else {
+            std::fprintf(stderr, "ERROR: Kernel::binned_data(): compiled binning supports 4- and 8-byte bin types\n");
+            return;
+        }
+    }
+    if (ctx.launched) *ctx.launched = true;
+}
 #endif
 }}  // namespace b200::dev
 
-template <typename data_t, typename bin_t = data_t> class Kernel {
+template <typename data_t, typename bin_t> class Kernel {
     IterationSpace<data_t> &iteration_space_;
     std::vector<AccessorBase *> inputs_;
     data_t reduction_result_{};
@@ -722,17 +934,22 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
     // device-side fields of the compiled-body path (filled right before the object is copied into the launch)
     data_t *d_out_ = nullptr;
     int d_out_stride_ = 0, d_ox_ = 0, d_oy_ = 0;
+    // what the last `bin(idx) = value` of a binning() body stored (dsl/kernel.hpp:62-64,126-129)
+    bin_t bin_val_{};
+    unsigned int bin_idx_ = 0;
 
     // identify the user's `reduce(left, right)` among {SUM, MIN, MAX, PROD} by evaluating it on probe values;
     // anything else has no device kernel
     int probe_reduce_mode() const {
-        const bin_t a1 = (bin_t)2, b1 = (bin_t)3, a2 = (bin_t)5, b2 = (bin_t)4;
-        const bin_t r1 = reduce(a1, b1), r2 = reduce(a2, b2), r3 = reduce(b1, a1);
-        if (r1 == (bin_t)5 && r2 == (bin_t)9) return HB_REDUCE_SUM;
-        if (r1 == (bin_t)2 && r2 == (bin_t)4 && r3 == (bin_t)2) return HB_REDUCE_MIN;
-        if (r1 == (bin_t)3 && r2 == (bin_t)5 && r3 == (bin_t)3) return HB_REDUCE_MAX;
-        if (r1 == (bin_t)6 && r2 == (bin_t)20) return HB_REDUCE_PROD;
-        return -1;
+        if constexpr (std::is_arithmetic<bin_t>::value) {
+            const bin_t a1 = (bin_t)2, b1 = (bin_t)3, a2 = (bin_t)5, b2 = (bin_t)4;
+            const bin_t r1 = reduce(a1, b1), r2 = reduce(a2, b2), r3 = reduce(b1, a1);
+            if (r1 == (bin_t)5 && r2 == (bin_t)9) return HB_REDUCE_SUM;
+            if (r1 == (bin_t)2 && r2 == (bin_t)4 && r3 == (bin_t)2) return HB_REDUCE_MIN;
+            if (r1 == (bin_t)3 && r2 == (bin_t)5 && r3 == (bin_t)3) return HB_REDUCE_MAX;
+            if (r1 == (bin_t)6 && r2 == (bin_t)20) return HB_REDUCE_PROD;
+        }
+        return -1;   // vector bins, or a reduce() that is none of the four
     }
 
     static bool check_requested() {
@@ -779,19 +996,26 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
     virtual ~Kernel() = default;
     HB_HD virtual void kernel() = 0;
     virtual b200::Lowering lower() { return {}; }
-    virtual bin_t reduce(bin_t, bin_t) const { assert(false && "No reduce method specified"); return {}; }
-    virtual void binning(unsigned int, unsigned int, data_t) { assert(false && "No binning method specified"); }  // dsl/kernel.hpp:91
+    HB_HD virtual bin_t reduce(bin_t, bin_t) const { assert(false && "No reduce method specified"); return {}; }
+    HB_HD virtual void binning(unsigned int, unsigned int, data_t) { assert(false && "No binning method specified"); }  // dsl/kernel.hpp:91
     virtual b200::Binning lower_binning() { return {}; }
     void add_accessor(AccessorBase *acc) { inputs_.push_back(acc); }
 
     // the typed launch hook of the compiled-body path: the macro at the end of this header overrides it in every Kernel
     // subclass that an nvcc-compiled translation unit defines.  false = this class has no device-compiled body.
     virtual void hb_dispatch_(const b200::dev::LaunchCtx &c) { if (c.launched) *c.launched = false; }
+    // compiled reduce() / binning() bodies (opt-in, -DHIPACC_B200_DEVICE_GLOBAL_OPS): same mechanism, hooked by the macros
+    // for `binning(...)`; results through c.result
+    virtual void hb_dispatch_global_(const b200::dev::LaunchCtx &c, int /*what*/, unsigned int /*num_bins*/, void * /*result*/) { if (c.launched) *c.launched = false; }
+    HB_HD unsigned int hb_bin_idx_() const { return bin_idx_; }
+    HB_HD const bin_t &hb_bin_val_() const { return bin_val_; }
+    void hb_set_num_bins_(unsigned int n) { num_bins_ = n; }
     void hb_fill_device_fields_(void *out_override) {
         const hb_view v = iteration_space_.rt().view();
         d_out_ = static_cast<data_t *>(out_override ? out_override : v.data);
         d_out_stride_ = v.stride; d_ox_ = v.offset_x; d_oy_ = v.offset_y;
     }
+    HB_HD data_t &hb_output_() { return output(); }
     int hb_is_width_() const { return iteration_space_.width(); }
     int hb_is_height_() const { return iteration_space_.height(); }
 
@@ -821,10 +1045,17 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
         if (!reduced_) {
             const int mode = probe_reduce_mode();
             if (mode < 0) {
-                std::fprintf(stderr, "ERROR: Kernel::reduced_data(): reduce() is not SUM/MIN/MAX/PROD; no device kernel, no host fallback\n");
-                return reduction_result_;
+                // not one of the library's four folds: the reduce() body itself, compiled for the device
+                bool launched = false;
+                hb_dispatch_global_(b200::dev::LaunchCtx{nullptr, nullptr, &launched}, 0, 0, &reduction_result_);
+                if (!launched) {
+                    std::fprintf(stderr, "ERROR: Kernel::reduced_data(): reduce() is not SUM/MIN/MAX/PROD and was not compiled for the device "
+                                         "(nvcc, -DHIPACC_B200_DEVICE_GLOBAL_OPS); no host fallback\n");
+                    return reduction_result_;
+                }
+            } else if constexpr (std::is_arithmetic<data_t>::value) {
+                reduction_result_ = hipaccApplyReduction<data_t>(iteration_space_.rt(), mode);
             }
-            reduction_result_ = hipaccApplyReduction<data_t>(iteration_space_.rt(), mode);
             reduced_ = true;
         }
         return reduction_result_;
@@ -834,19 +1065,28 @@ template <typename data_t, typename bin_t = data_t> class Kernel {
     bin_t *binned_data(const unsigned int num_bins) {
         if (!executed_) execute();
         const b200::Binning b = lower_binning();
-        if (b.index_kind < 0 || probe_reduce_mode() != HB_REDUCE_SUM || sizeof(bin_t) != 4) {
-            std::fprintf(stderr, "ERROR: Kernel::binned_data(): needs lower_binning() and reduce() == left + right on 32-bit bins; "
-                                 "no device kernel otherwise, no host fallback\n");
-            return new bin_t[num_bins]();
-        }
         num_bins_ = num_bins;
-        return hipaccApplyBinning<data_t, bin_t>(iteration_space_.rt(), num_bins, b.index_kind, b.value_kind, b.p0);
+        if constexpr (sizeof(bin_t) == 4 && std::is_arithmetic<data_t>::value) {
+            if (b.index_kind >= 0 && probe_reduce_mode() == HB_REDUCE_SUM)
+                return hipaccApplyBinning<data_t, bin_t>(iteration_space_.rt(), num_bins, b.index_kind, b.value_kind, b.p0);
+        }
+        // any other binning() / reduce() pair: the bodies themselves, compiled for the device
+        bin_t *bins = new bin_t[num_bins]();
+        bool launched = false;
+        hb_dispatch_global_(b200::dev::LaunchCtx{nullptr, nullptr, &launched}, 1, num_bins, bins);
+        if (!launched)
+            std::fprintf(stderr, "ERROR: Kernel::binned_data(): needs lower_binning() with reduce() == left + right on 32-bit bins, or binning() / "
+                                 "reduce() compiled for the device (nvcc, -DHIPACC_B200_DEVICE_GLOBAL_OPS); no host fallback\n");
+        return bins;
     }
 
   protected:
     unsigned int num_bins_ = 0;
-    unsigned int num_bins() const { return num_bins_; }
-    bin_t &bin(const unsigned int) { b200::host_body_called(); }
+    HB_HD unsigned int num_bins() const { return num_bins_; }
+    HB_HD bin_t &bin(const unsigned int idx) {
+        bin_idx_ = idx;
+        return bin_val_;
+    }
 
     // ---- kernel()-body vocabulary: device code under nvcc, never run on the host -------------------------------------
     HB_HD data_t &output() {
@@ -978,11 +1218,36 @@ inline void traverse(int loop = 1, const std::function<void()> &f = [] {}) { hip
 // so that sample sources compile unmodified (dsl/kernel.hpp:79 declares `virtual void kernel() = 0`).
 // ---------------------------------------------------------------------------------------------------
 #ifdef HIPACC_B200_DEVICE_DSL
-#define kernel()                                                                       \
+// `kernel()` with no arguments is the member declaration; `kernel(args)` -- a variable that happens to be called kernel,
+// as in samples-public/5_Other/Game_of_Life -- is left alone.
+#define kernel(...) HB_KERNEL_##__VA_OPT__(ARGS)(__VA_ARGS__)
+#define HB_KERNEL_ARGS(...) kernel(__VA_ARGS__)
+#define HB_KERNEL_()                                                                   \
     hb_dispatch_(const ::hipacc::b200::dev::LaunchCtx &hb_ctx_) override {             \
         ::hipacc::b200::dev::launch_generic(*this, hb_ctx_);                           \
     }                                                                                  \
     __host__ __device__ void kernel()
+
+// Opt-in (-DHIPACC_B200_DEVICE_GLOBAL_OPS): the members `void binning(x, y, pixel)` and `bin_t reduce(left, right) const`
+// become __host__ __device__ as well, so that binned_data() / reduced_data() can run ANY binning / fold on the device
+// (dsl_binning_kernel / dsl_reduce_kernel).  `binning(...)` with three parameters is the declaration (it also carries the
+// typed launch hook); `reduce(a, b)` with exactly two arguments is the declaration, every other arity -- the reduce(dom,
+// mode, lambda) calls inside kernel() bodies -- passes through untouched.
+#ifdef HIPACC_B200_DEVICE_GLOBAL_OPS
+#define HB_CAT_(a, b) a##b
+#define HB_CAT(a, b) HB_CAT_(a, b)
+#define HB_ARITY_(a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15, a16, N, ...) N
+#define HB_ARITY(...) HB_ARITY_(__VA_ARGS__, M, M, M, M, M, M, M, M, M, M, M, M, M, M, 2, 1, 0)
+#define reduce(...) HB_CAT(HB_REDUCE_, HB_ARITY(__VA_ARGS__))(__VA_ARGS__)
+#define HB_REDUCE_2(a, b) __host__ __device__ reduce(a, b)
+#define HB_REDUCE_1(a) reduce(a)
+#define HB_REDUCE_M(...) reduce(__VA_ARGS__)
+#define binning(...)                                                                                                        \
+    hb_dispatch_global_(const ::hipacc::b200::dev::LaunchCtx &hb_ctx_, int hb_what_, unsigned int hb_bins_, void *hb_res_) override { \
+        ::hipacc::b200::dev::launch_global(*this, hb_ctx_, hb_what_, hb_bins_, hb_res_);                                     \
+    }                                                                                                                       \
+    __host__ __device__ void binning(__VA_ARGS__)
+#endif
 #endif
 
 #endif  // HIPACC_B200_DSL_HPP

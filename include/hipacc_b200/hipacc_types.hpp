@@ -154,6 +154,16 @@ HB_VEC_CONVERT(uint4)
 HB_VEC_CONVERT(float4)
 #undef HB_VEC_CONVERT
 
+// ---- as_float / convert<T> (dsl/types.hpp:103-125): what the interpolating accessors compute in -------------------------
+namespace hipacc_b200 {
+template <typename T, typename = void> struct float_of { typedef float type; };
+template <typename T> struct float_of<T, typename std::enable_if<vec4<T>::is>::type> { typedef float4 type; };
+template <typename T, typename std::enable_if<!vec4<T>::is, int>::type = 0> HB_HD float to_float(T v) { return (float)v; }
+template <typename V, if_vec<V> = 0> HB_HD float4 to_float(V v) { return mk<float4>(v.x, v.y, v.z, v.w); }
+template <typename T, typename std::enable_if<!vec4<T>::is, int>::type = 0> HB_HD T from_float(float v) { return (T)v; }
+template <typename V, if_vec<V> = 0> HB_HD V from_float(float4 v) { return mk<V>(v.x, v.y, v.z, v.w); }
+}  // namespace hipacc_b200
+
 // ---- element-wise math of hipacc::math on vectors (dsl/math_functions.hpp): min, max with vector or scalar bound, the
 // float functions on float4.  Declared at global scope like the reference's; hipacc::math pulls them in. ---------------
 #define HB_VEC_MINMAX(NAME, CMP)                                                                                        \

@@ -16,7 +16,7 @@
 //   IS / accessor offset arithmetic      lib/AST/MemoryAccess.cpp:98-177, dsl/image.hpp:412
 //   boundary index remap and its order   lib/AST/BorderHandling.cpp:41-120,339-366
 //   tap order / fold                     lib/AST/Convolution.cpp:90-99,397-435, dsl/kernel.hpp:241-315
-//   interpolation (NN, LF)               dsl/image.hpp:390-422, lib/AST/Interpolate.cpp:85-113
+//   interpolation (NN, LF, B5, CF, L3)    dsl/image.hpp:321-528, lib/AST/Interpolate.cpp:85-113
 //   global reduction                     dsl/kernel.hpp:121-151, runtime/hipacc_cpu_red.hpp:19-68
 // Build: g++ -O3 -fopenmp -ffp-contract=off -mno-fma  (no FMA contraction: float results
 // equal the DSL's unfused multiply + add).
@@ -241,6 +241,26 @@ int bilateral_typed(const hb_bilateral_desc &d) {
 }
 
 // ------------------------------------------------------------------ point operators
+// interpolation weights (dsl/image.hpp:321-383)
+inline float interp_binomial5(float diff) {
+    diff = std::fabs(diff);
+    return diff < 0.5f ? 6.0f / 8.0f : diff < 1.0f ? 4.0f / 8.0f : diff < 1.5f ? 1.0f / 8.0f : 0.0f;
+}
+inline float interp_bicubic(float diff) {   // Keys' cubic convolution, a = -0.5
+    diff = std::fabs(diff);
+    const float a = -0.5f;
+    if (diff < 1.0f) return (a + 2.0f) * diff * diff * diff - (a + 3.0f) * diff * diff + 1.0f;
+    if (diff < 2.0f) return a * diff * diff * diff - 5.0f * a * diff * diff + 8.0f * a * diff - 4.0f * a;
+    return 0.0f;
+}
+inline float interp_lanczos3(float diff) {   // evaluated in double, rounded once (image.hpp:366-382)
+    diff = std::fabs(diff);
+    const float l = 3.0f;
+    const double pi = std::atan(1.0) * 4;
+    if (diff == 0.0f) return 1.0f;
+    if (diff < l) return static_cast<float>(l * (std::sin(pi * diff / l) * std::sin(pi * diff)) / (pi * pi * diff * diff));
+    return 0.0f;
+}
 // value of input `v` for output pixel (gx,gy) of an IS of size (isw,ish), through the
 // accessor's interpolation mode (dsl/image.hpp:390-422), default boundary CLAMP (:616-620)
 template <typename T>
@@ -256,10 +276,37 @@ inline float fetch_f(const Img<T> &im, const hb_view &v, int interp, int gx, int
     if (yb < 0.0f) yb = 0.0f;
     const int x_int = (int)xb, y_int = (int)yb;
     const float x_frac = xb - x_int, y_frac = yb - y_int;
-    const float r = (1.0f - x_frac) * (1.0f - y_frac) * (float)im.at(x_int, y_int) +
-                    x_frac * (1.0f - y_frac) * (float)im.at(x_int + 1, y_int) +
-                    (1.0f - x_frac) * y_frac * (float)im.at(x_int, y_int + 1) +
-                    x_frac * y_frac * (float)im.at(x_int + 1, y_int + 1);
+    if (interp == HB_INTERP_LF) {
+        const float r = (1.0f - x_frac) * (1.0f - y_frac) * (float)im.at(x_int, y_int) +
+                        x_frac * (1.0f - y_frac) * (float)im.at(x_int + 1, y_int) +
+                        (1.0f - x_frac) * y_frac * (float)im.at(x_int, y_int + 1) +
+                        x_frac * y_frac * (float)im.at(x_int + 1, y_int + 1);
+        return r;
+    }
+    // B5 / CF / L3 (dsl/image.hpp:424-528): a TAPS x TAPS neighbourhood starting at (x_int + X0, y_int + Y0); every row is
+    // the left-to-right sum of pixel * wx[i], the result the top-to-bottom sum of row * wy[j]
+    const int taps = interp == HB_INTERP_L3 ? 6 : 4;
+    const int x0 = interp == HB_INTERP_B5 ? 0 : interp == HB_INTERP_CF ? -1 : -2;
+    const int y0 = interp == HB_INTERP_B5 ? 0 : -1;   // L3 starts its rows at y_int - 1 like CF (image.hpp:478,484,...)
+    float wx[6][6], wy[6];
+    float fx = x_frac, fy = y_frac;
+    if (interp == HB_INTERP_B5) { fx += 0.5; fy += 0.5; }
+    for (int j = 0; j < taps; ++j) {
+        for (int i = 0; i < taps; ++i) {
+            if (interp == HB_INTERP_B5) wx[j][i] = interp_binomial5(fx - i);
+            else if (interp == HB_INTERP_CF) wx[j][i] = interp_bicubic(fx - 1 + i);
+            else wx[j][i] = interp_lanczos3(fx - 2 + ((j == 1 && i == 4) ? 5 : i));   // row 1 repeats the weight of tap 5 (image.hpp:489)
+        }
+        wy[j] = interp == HB_INTERP_B5 ? interp_binomial5(fy - j) : interp == HB_INTERP_CF ? interp_bicubic(fy - 1 + j) : interp_lanczos3(fy - 2 + j);
+    }
+    float rows[6];
+    for (int j = 0; j < taps; ++j) {
+        float acc = (float)im.at(x_int + x0, y_int + y0 + j) * wx[j][0];
+        for (int i = 1; i < taps; ++i) acc = acc + (float)im.at(x_int + x0 + i, y_int + y0 + j) * wx[j][i];
+        rows[j] = acc;
+    }
+    float r = rows[0] * wy[0];
+    for (int j = 1; j < taps; ++j) r = r + rows[j] * wy[j];
     return r;
 }
 // the accessor returns data_t: interpolated value converted back (convert<T>, dsl/types.hpp:115-117)

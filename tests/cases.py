@@ -111,3 +111,8 @@ def single_tap_spec(dx, dy, size, boundary, const=0.0):
     dom[size // 2 + dy, size // 2 + dx] = 1
     return S.LocalSpec(size, size, A.REDUCE_DOMAIN, A.SUM, A.TAP_IN, A.S32, None, dom, boundary, const,
                        A.EPI_CAST, (0, 0, 0), A.U8)
+
+
+# tests/golden/reference_interp.npz (generate.py: INTERP_SHAPE / INTERP_TARGETS, kept equal)
+INTERP_SHAPE = (29, 37)
+INTERP_TARGETS = [(58, 74), (20, 19), (41, 50)]

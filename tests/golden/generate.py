@@ -101,8 +101,26 @@ def rgba():
     print("wrote", len(out), "arrays to reference_rgba.npz")
 
 
+INTERP_SHAPE = (29, 37)
+INTERP_TARGETS = [(58, 74), (20, 19), (41, 50)]   # 2x up, a ragged down-scale, a non-integer up-scale
+
+
+def interp():
+    """reference_interp.npz: a copy kernel through an interpolating Accessor (B5 / CF / L3; dsl/image.hpp:424-528) executed
+    by the reference DSL -- the Scaling sample's operator with the three wide modes."""
+    out = {}
+    img = (synth.image_np("float32", INTERP_SHAPE[1], INTERP_SHAPE[0], seed=5) * 255).astype(np.float32)
+    for mode, name in ((A.INTERP_B5, "b5"), (A.INTERP_CF, "cf"), (A.INTERP_L3, "l3")):
+        for oh, ow in INTERP_TARGETS:
+            out[f"{name}_{oh}x{ow}"] = O.ref_interp_f32(img, ow, oh, mode)
+    np.savez_compressed(os.path.join(HERE, "reference_interp.npz"), **out)
+    print("wrote", len(out), "arrays to reference_interp.npz")
+
+
 if __name__ == "__main__":
-    if "--only-hist" in sys.argv:
+    if "--only-interp" in sys.argv:
+        interp()
+    elif "--only-hist" in sys.argv:
         hist()
     elif "--only-rgba" in sys.argv:
         rgba()
@@ -110,3 +128,4 @@ if __name__ == "__main__":
         main()
         hist()
         rgba()
+        interp()

@@ -91,6 +91,31 @@ def test_front_headers_need_no_cuda_toolkit():
     assert "cuda" not in r.stdout.lower(), r.stdout
 
 
+# ------------------------------------------------------------------ the reference's own sample programs, unmodified
+import ref_samples  # noqa: E402  (tests/ref_samples.py)
+
+
+@pytest.mark.skipif(not ref_samples.have_reference(), reason="the reference tree exists in the build container only")
+def test_reference_samples_build_unmodified():
+    """every sample of samples-public/ in ref_samples.SAMPLES compiles against the B200 front without touching its source"""
+    failed = ref_samples.build_all()
+    assert not failed, "\n".join(f"{k}:\n{v[-1500:]}" for k, v in failed.items())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sample", sorted(ref_samples.SAMPLES))
+def test_reference_sample_runs_on_device(sample):
+    """the sample's own main(): its DSL kernels run on the B200, its embedded plain C reference decides PASSED / FAILED"""
+    exe = os.path.join(ref_samples.OUT, ref_samples.name_of(sample))
+    if not os.path.exists(exe):
+        pytest.skip("binary not built (tests/ref_samples.py builds it where /root/reference exists)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, cwd=ref_samples.OUT)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "FAILED" not in out and "ERROR" not in out, out[-3000:]
+    if ref_samples.SAMPLES[sample] == "PASSED":
+        assert "Test PASSED" in out, out[-3000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CU_PROGRAMS)
 def test_compiled_body_program_runs_on_device(name):

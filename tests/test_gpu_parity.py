@@ -6,6 +6,8 @@
 Bar: bit-exact for uchar / int / index work AND for float stencils (separately rounded mul/add);
 1e-5 relative for kernels with expf / division chains; float SUM within 1e-5 of the float64 sum.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -224,6 +226,35 @@ def test_interpolation(hb, oracle, dev, shape):
     np.testing.assert_array_equal(nn, oracle.point_op(A.POINT_COPY, [f], A.F32, (ch, cw), [A.INTERP_NN]))
     lf = to_np(hb.point_op(A.POINT_COPY, [to_dev(hb, nn, dev)], A.F32, (h, w), [A.INTERP_LF]))
     np.testing.assert_array_equal(lf, oracle.point_op(A.POINT_COPY, [nn], A.F32, (h, w), [A.INTERP_LF]))
+
+
+@pytest.mark.parametrize("mode", [A.INTERP_B5, A.INTERP_CF, A.INTERP_L3])
+def test_wide_interpolation(hb, oracle, dev, mode):
+    """B5 / CF / L3 at arbitrary scale factors: golden from the reference DSL, then float and integer images against the
+    oracle.  B5 / CF are pure float arithmetic (bit-exact); L3's weights go through a double-precision sin (1e-5)."""
+    G = cases
+    g = np.load(os.path.join(os.path.dirname(cases.GOLDEN_PATH), "reference_interp.npz"))
+    name = {A.INTERP_B5: "b5", A.INTERP_CF: "cf", A.INTERP_L3: "l3"}[mode]
+    img = (synth.image_np("float32", G.INTERP_SHAPE[1], G.INTERP_SHAPE[0], seed=5) * 255).astype(np.float32)
+    def close(got, want, what):
+        if mode == A.INTERP_L3:
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4, err_msg=what)
+        else:
+            np.testing.assert_array_equal(got, want, err_msg=what)
+    for oh, ow in G.INTERP_TARGETS:
+        close(to_np(hb.point_op(A.POINT_COPY, [to_dev(hb, img, dev)], A.F32, (oh, ow), [mode])), g[f"{name}_{oh}x{ow}"], f"golden {oh}x{ow}")
+    f = synth.image_np("float32", 333, 211, seed=36)
+    for oh, ow in ((422, 666), (97, 150), (211, 333), (500, 123)):
+        close(to_np(hb.point_op(A.POINT_COPY, [to_dev(hb, f, dev)], A.F32, (oh, ow), [mode])),
+              oracle.point_op(A.POINT_COPY, [f], A.F32, (oh, ow), [mode]), f"f32 {oh}x{ow}")
+    u8 = synth.image_np("uint8", 200, 120, seed=37)
+    got = to_np(hb.point_op(A.POINT_COPY, [to_dev(hb, u8, dev)], A.U8, (171, 333), [mode])).astype(np.int32)
+    want = oracle.point_op(A.POINT_COPY, [u8], A.U8, (171, 333), [mode]).astype(np.int32)
+    if mode == A.INTERP_L3:
+        # a 1-ulp weight difference can move a value across an integer: at most 1 LSB, and only rarely
+        assert np.abs(got - want).max() <= 1 and (got != want).mean() < 1e-3
+    else:
+        np.testing.assert_array_equal(got, want)
 
 
 def test_interpolation_kat(hb, dev):
