@@ -257,6 +257,9 @@ int hb_point_op(const hb_point_desc *desc, void *stream);
  * reference; the scalar is written to *result_host in the view's dtype.
  * MIN/MAX are bit-exact; float SUM is accumulated pairwise (float per thread, double across
  * threads) -- see DESIGN.md for why the reference's serial float fold is not a stable target.
+ * Non-finite pixels: MIN / MAX are the IEEE minimum / maximum of the pixels that are numbers (a NaN never wins; +-inf take
+ * part normally); SUM / PROD propagate NaN and inf as the arithmetic does.  The DSL's `l < r ? l : r` fold returns a value
+ * that depends on where in the iteration order a NaN sits, which no parallel fold (the reference's included) reproduces.
  */
 int hb_reduce(const hb_view *in, int reduce_mode, void *result_host, void *stream);
 /* fused single pass over HBM: out[0]=min out[1]=max out[2]=sum (f32 images) */

@@ -181,10 +181,8 @@ def reduce_minmaxsum(img, roi=None):
 def local_op_x4(spec, img, **kw):
     """uchar4 image [H, W, 4]: the DSL's float4 / int4 arithmetic and convert_uchar4() are element-wise
     (dsl/types.hpp:56-516), so a local operator on uchar4 pixels is the scalar operator on each channel plane."""
-    out = np.empty_like(img)
-    for c in range(4):
-        out[..., c] = local_op(spec, np.ascontiguousarray(img[..., c]), **kw)
-    return out
+    planes = [local_op(spec, np.ascontiguousarray(img[..., c]), **kw) for c in range(4)]
+    return np.ascontiguousarray(np.stack(planes, axis=-1))   # the spec's output type: uchar4 -> uchar4 / short4 / int4, float4 -> float4
 
 
 def binning(img, num_bins, index_kind=A.BIN_INDEX_SCALE, value_kind=A.BIN_VALUE_ONE, p0=255.0, roi=None):

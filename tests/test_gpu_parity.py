@@ -665,6 +665,29 @@ def test_rgba_point_ops_and_padded_rows(hb, oracle, dev):
     np.testing.assert_array_equal(to_np(hb.local_op(spec, buf[:, :130])), oracle.local_op_x4(spec, img))
 
 
+@pytest.mark.parametrize("b", [A.CLAMP, A.MIRROR, A.CONSTANT])
+def test_four_channel_intermediates_and_float4(hb, oracle, dev, b):
+    """the other 4-channel pixel types (dsl/types.hpp): Sobel_RGBA's uchar4 -> int4 derivative and its int4, int4 -> uchar4
+    combine (samples-public/3_Preprocessing/Sobel_RGBA/src/main.cpp:55-98), a uchar4 -> short4 derivative, float4 -> float4"""
+    img = cases.rgba_image(61, 83, seed=29)
+    d = to_dev(hb, img, dev)
+    sx, sy = S.sobel_u8(M.SOBEL3_X, b), S.sobel_u8(M.SOBEL3_Y, b)
+    gx, gy = hb.local_op(sx, d), hb.local_op(sy, d)
+    assert str(gx.dtype) == "torch.int32" and tuple(gx.shape) == (61, 83, 4)
+    wx, wy = oracle.local_op_x4(sx, img), oracle.local_op_x4(sy, img)
+    np.testing.assert_array_equal(to_np(gx), wx)
+    np.testing.assert_array_equal(to_np(gy), wy)
+    mag = to_np(hb.point_op(A.POINT_SOBEL_COMBINE, [gx, gy], A.U8, p=(4, 0)))
+    want = np.stack([oracle.point_op(A.POINT_SOBEL_COMBINE, [np.ascontiguousarray(wx[..., c]), np.ascontiguousarray(wy[..., c])], A.U8, p=(4, 0))
+                     for c in range(4)], axis=-1)
+    np.testing.assert_array_equal(mag, want)
+    hd = S.harris_deriv(M.HARRIS_DX)
+    np.testing.assert_array_equal(to_np(hb.local_op(hd, d)), oracle.local_op_x4(hd, img))   # short4 out
+    f4 = np.ascontiguousarray(synth.image_np("float32", 70 * 4, 45, seed=30).reshape(45, 70, 4))
+    for spec in (S.convolve_f32(M.GAUSS5, b), S.domain_reduce_f32(M.LAPLACE3.astype(np.float32), b)):
+        np.testing.assert_array_equal(to_np(hb.local_op(spec, to_dev(hb, f4, dev))), oracle.local_op_x4(spec, f4))
+
+
 def test_rgba_full_size_sample_shape(hb, oracle, dev):
     """Gaussian_Blur_RGBA's own size (4032 x 3024 uchar4): windows against the per-channel oracle"""
     import torch
@@ -902,6 +925,78 @@ def test_full_size_c4_harris_strip_of_32k(hb, oracle, dev):
     """One 32768-wide strip (the per-GPU share at 8 GPUs is 32768 x 4096): fused kernel vs oracle pipeline."""
     img = synth.image_np("uint8", 32768, 512, seed=4)
     np.testing.assert_array_equal(to_np(hb.harris(to_dev(hb, img, dev))), oracle.harris(img))
+
+
+def test_full_size_c4_harris_32768_windows(hb, oracle, dev):
+    """The release configuration itself: the fused Harris kernel on the whole 32768 x 32768 image (1 GiB in, 1 GiB out),
+    checked bit for bit against the oracle's 9-kernel pipeline on windows at the four corners, at the row-strip edges of
+    the 2 / 4 / 8 GPU partitions and in the interior.  A window's own borders are valid only where they are image borders,
+    so every window is computed with an 8-pixel margin that is cut off unless it is the image edge."""
+    n, H, W, m = 32768, 96, 640, 8
+    img = hb.empty_image(A.U8, n, n, device=dev)
+    for y in range(0, n, 4096):   # generated on the device, strip by strip
+        img[y:y + 4096].copy_(synth.image_torch("uint8", n, 4096, seed=4, y0=y, device=dev))
+    out = hb.harris(img)
+    wins = [(0, 0), (0, n - W), (n - H, 0), (n - H, n - W), (16000, 16000), (7777, 30001)]
+    wins += [(k * 4096 - H // 2, x) for k in range(1, 8) for x in (0, 12345, n - W)]   # strip edges of every partition
+    for (y0, x0) in wins:
+        ys, xs = slice(max(0, y0 - m), min(n, y0 + H + m)), slice(max(0, x0 - m), min(n, x0 + W + m))
+        crop = synth.image_np("uint8", xs.stop - xs.start, ys.stop - ys.start, seed=4, x0=xs.start, y0=ys.start)
+        want = oracle.harris(crop)
+        oy, ox = y0 - ys.start, x0 - xs.start
+        np.testing.assert_array_equal(to_np(out[y0:y0 + H, x0:x0 + W]), want[oy:oy + H, ox:ox + W], err_msg=f"window at ({y0}, {x0})")
+    assert 0 < int(out[:4096].sum().item())   # the detector fires
+
+
+def test_full_size_c5_pyramid_down_pass_windows(hb, oracle, dev):
+    """16384 x 16384, the fused down step (blur + subsample + DoG) at full size for three transitions: gaus(1..3) and
+    lap(0..2) are local functions of the input, so windows of them are compared bit for bit with the oracle's unfused
+    operators run on crops of the level-0 image (corners, partition edges, interior).  Crops start on multiples of 64 so
+    that every level's sampling grid coincides with the global one."""
+    n, S0, m = 16384, 512, 64
+    g = [hb.empty_image(A.F32, n, n, device=dev)]
+    for y in range(0, n, 2048):
+        g[0][y:y + 2048].copy_(synth.image_torch("float32", n, 2048, seed=5, y0=y, device=dev))
+    lap = []
+    for l in range(1, 4):
+        g.append(hb.empty_image(A.F32, n >> l, n >> l, device=dev))
+        lap.append(hb.empty_image(A.F32, n >> (l - 1), n >> (l - 1), device=dev))
+        hb.pyr_down(g[l - 1], g[l], M.GAUSS5, lap_fine=lap[l - 1])
+    blur = S.convolve_f32(M.GAUSS5, A.CLAMP)
+    for (y0, x0) in [(0, 0), (0, n - S0), (n - S0, 0), (n - S0, n - S0), (8192 - 256, 4096), (2048 - 256, n - S0), (6144, 8192 - 256)]:
+        ys, xs = slice(max(0, y0 - m), min(n, y0 + S0 + m)), slice(max(0, x0 - m), min(n, x0 + S0 + m))
+        og = [synth.image_np("float32", xs.stop - xs.start, ys.stop - ys.start, seed=5, x0=xs.start, y0=ys.start)]
+        ol = []
+        for l in range(1, 4):   # the sample's way down (Gaussian_Laplacian_Pyramid/src/main.cpp:199-225), unfused
+            tmp = oracle.local_op(blur, og[l - 1])
+            og.append(oracle.point_op(A.POINT_COPY, [tmp], A.F32, (og[l - 1].shape[0] // 2, og[l - 1].shape[1] // 2), [A.INTERP_NN]))
+            ol.append(oracle.point_op(A.POINT_SUB, [og[l - 1], og[l]], A.F32, og[l - 1].shape, [A.INTERP_NO, A.INTERP_LF]))
+        for l in range(0, 4):
+            # the window at level l, shrunk by 8 pixels where the crop side is not an image side (the crop's own CLAMP)
+            a0, a1 = (y0 >> l) + (8 if ys.start > 0 else 0), ((y0 + S0) >> l) - (8 if ys.stop < n else 0)
+            b0, b1 = (x0 >> l) + (8 if xs.start > 0 else 0), ((x0 + S0) >> l) - (8 if xs.stop < n else 0)
+            cy, cx = ys.start >> l, xs.start >> l
+            if l >= 1:
+                np.testing.assert_array_equal(to_np(g[l][a0:a1, b0:b1]), og[l][a0 - cy:a1 - cy, b0 - cx:b1 - cx], err_msg=f"gaus({l}) window ({y0}, {x0})")
+            if l <= 2:
+                np.testing.assert_array_equal(to_np(lap[l][a0:a1, b0:b1]), ol[l][a0 - cy:a1 - cy, b0 - cx:b1 - cx], err_msg=f"lap({l}) window ({y0}, {x0})")
+
+
+def test_reduce_min_max_with_nan_pixels(hb, dev):
+    """Contract for non-finite input (include/hipacc_b200.h, hb_reduce): MIN / MAX are the IEEE minimum / maximum of the
+    pixels that are numbers -- a NaN pixel never wins -- and +-inf take part normally.  (The DSL's `l < r ? l : r` fold
+    returns a value that depends on WHERE the NaN sits in the iteration order, which no parallel reduction reproduces;
+    the reference's own CUDA reduction does not either, runtime/hipacc_cu_red.hpp:140-346.)"""
+    f = synth.image_np("float32", 700, 300, seed=50) - np.float32(0.5)
+    f[17, 333] = np.nan
+    f[0, 0] = np.nan
+    f[299, 699] = np.nan
+    f[100, 100] = np.inf
+    mn, mx, _ = hb.reduce_minmaxsum(to_dev(hb, f, dev))
+    assert np.float32(mn) == np.nanmin(f) and np.float32(mx) == np.inf
+    assert np.float32(hb.reduce(to_dev(hb, f, dev), A.MIN)) == np.nanmin(f)
+    f[100, 100] = -np.inf
+    assert np.float32(hb.reduce(to_dev(hb, f, dev), A.MIN)) == -np.inf and np.float32(hb.reduce(to_dev(hb, f, dev), A.MAX)) == np.nanmax(f)
 
 
 def test_full_size_c5_pyramid_properties(hb, dev):
