@@ -452,7 +452,7 @@ def main():
 
     operators = named_operators(hb, dev, world, rank, stream, halo is not None, peak, parity, args)
     if args.extra:
-        operators.update(extra_operators(hb, dev, peak) if world == 1 else extra_sharded(hb, dev, world, rank, stream, halo is not None))
+        operators.update(extra_operators(hb, dev, peak, use_graph=not args.no_graph) if world == 1 else extra_sharded(hb, dev, world, rank, stream, halo is not None))
 
     sharded_parity = None
     if world > 1 and parity:
@@ -662,7 +662,7 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
     return res
 
 
-def extra_operators(hb, dev, peak):
+def extra_operators(hb, dev, peak, use_graph=True):
     """Gpixels/s and HBM fraction of the other BASELINE.json configs on one GPU (kernel-only, CUDA events)."""
     import numpy as np
     import torch
@@ -679,6 +679,7 @@ def extra_operators(hb, dev, peak):
                 fn()
             torch.cuda.synchronize()
             run, n = fn, reps
+            graph = graph and use_graph   # --no-graph (profiling passes): plain launches
             if graph:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
