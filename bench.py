@@ -601,7 +601,8 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
     pl = hb.Pyramid(hb.empty_image(A.F32, Wp, Hp, device=dev).zero_(), depth)
     sp = None
     if world > 1:   # sharded traversal first (its parity reference is the FIRST unsharded traversal of the same input)
-        plan = strips.PyramidShardPlan(Wp, Hp, depth, world, rank, 5)
+        # HB_C5_SPLIT_DOG=1: the DifferenceOfGaussian of the sharded levels runs on a second stream, off the latency-bound chain
+        plan = strips.PyramidShardPlan(Wp, Hp, depth, world, rank, 5, split_dog=bool(int(os.environ.get("HB_C5_SPLIT_DOG", "0"))))
         sp = strips.ShardedPyramid(plan, dev, hb=hb if p2p else None)
         if p2p:
             sp.enable_p2p(hb)
@@ -641,7 +642,7 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
                          f"({Wp >> plan.G}x{Hp >> plan.G}) per traversal, levels >= {plan.G} replicated, extension rows recomputed instead of exchanged; "
                          "single_gpu_ms = the unsharded traversal on this rank's GPU in the same run"}
         if os.environ.get("HB_BENCH_PHASES") and p2p:   # diagnosis: GPU-timer marks between the kernels of the captured traversal
-            for mode in (False, True, "edges_on_side"):
+            for mode in (False, True):
                 marks = torch.zeros(16, dtype=torch.int64, device=dev)
                 gfn, _ = graphed(lambda: sp.traverse(hb, M.GAUSS5, stream=stream, marks=marks, overlap=mode))
                 acc = None

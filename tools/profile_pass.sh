@@ -14,6 +14,8 @@ capture() {  # kernel regex, launches to skip, tag, source page?
   ncu -i $OUT/full_$3.ncu-rep --page raw --csv > $OUT/full_$3.raw.csv 2>/dev/null
   [ "$4" = "src" ] && ncu -i $OUT/full_$3.ncu-rep --page source --csv > $OUT/full_$3.source.csv 2>/dev/null
   python tools/ncu_keys.py $OUT/full_$3.raw.csv > $OUT/full_$3.txt 2>&1
+  [ "$4" = "src" ] && python tools/ncu_opmix.py $OUT/full_$3.source.csv > $OUT/full_$3.opmix.txt 2>&1
+  rm -f $OUT/full_$3.ncu-rep   # gpurun copies at most 64 MiB back; the raw / source CSV pages carry what profiles/ keeps
   echo "== $3"; grep -E "Kernel Name|gpu__time_duration|dram__bytes|issue_active|registers_per_thread" $OUT/full_$3.txt
 }
 capture local_tma_f32_kernel 3 local_tma
