@@ -16,7 +16,7 @@ from . import masks, specs, synth  # noqa: F401  (re-exported)
 from ._abi import *  # noqa: F401,F403  (enum constants)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhipacc_b200.so")
+LIB_PATH = os.environ.get("HIPACC_B200_LIB") or os.path.join(_HERE, "lib", "libhipacc_b200.so")   # the override is for A/B builds (tools/)
 _lib = None
 
 
