@@ -88,6 +88,15 @@ __device__ __forceinline__ int &iter_state(int slot) {
 #endif
 
 #ifdef __CUDACC__
+// A device-side field of a snapshot object.  The objects live in the launch's arena in GLOBAL memory and nothing writes
+// them during the kernel, but the compiler only sees a generic `this` that might alias the shared-memory cells of
+// iter_state: without help it reloads every field after every seek.  ld.global.nc says "read-only for this kernel".
+template <typename T> __device__ __forceinline__ T fld(const T &f) {
+    if constexpr (sizeof(T) == 4) { const unsigned v = __ldg(reinterpret_cast<const unsigned *>(&f)); T r; memcpy(&r, &v, 4); return r; }
+    else if constexpr (sizeof(T) == 8) { const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long *>(&f)); T r; memcpy(&r, &v, 8); return r; }
+    else if constexpr (sizeof(T) == 1) { const unsigned char v = __ldg(reinterpret_cast<const unsigned char *>(&f)); T r; memcpy(&r, &v, 1); return r; }
+    else return f;
+}
 constexpr int kInterpSlots = 4;    // interpolating Accessors one kernel() body may read
 // size of the iteration space (the interpolating accessors scale by it), published by every thread of the CTA
 __device__ __forceinline__ int *is_dims() {
@@ -246,21 +255,23 @@ class MaskBase {
     // offset of the current iteration step relative to the centre (dsl/mask.hpp:100-110)
     HB_HD int x() const {
 #ifdef __CUDA_ARCH__
-        return (short)(b200::dev::iter_state(d_slot_) & 0xffff);
+        return (short)(b200::dev::iter_state(b200::dev::fld(d_slot_)) & 0xffff);
 #else
         b200::host_body_called();
 #endif
     }
     HB_HD int y() const {
 #ifdef __CUDA_ARCH__
-        return b200::dev::iter_state(d_slot_) >> 16;
+        return b200::dev::iter_state(b200::dev::fld(d_slot_)) >> 16;
 #else
         b200::host_body_called();
 #endif
     }
 #ifdef __CUDA_ARCH__
-    __device__ __forceinline__ void dev_seek(int dx, int dy) const { b200::dev::iter_state(d_slot_) = (dy << 16) | (dx & 0xffff); }
-    __device__ __forceinline__ bool dev_visited(int k) const { return d_domain_[k] != 0; }
+    __device__ __forceinline__ void dev_seek(int dx, int dy) const { b200::dev::iter_state(b200::dev::fld(d_slot_)) = (dy << 16) | (dx & 0xffff); }
+    __device__ __forceinline__ bool dev_visited(int k) const { return __ldg(b200::dev::fld(d_domain_) + k) != 0; }
+    __device__ __forceinline__ int dev_size_x() const { return b200::dev::fld(size_x_); }
+    __device__ __forceinline__ int dev_size_y() const { return b200::dev::fld(size_y_); }
 #endif
 };
 
@@ -327,21 +338,24 @@ template <typename data_t> class Mask : public MaskBase {
     // kernel()-body forms: mask(), mask(dom), mask(x, y)
     HB_HD data_t operator()() const {
 #ifdef __CUDA_ARCH__
-        return d_coef_[(y() + size_y_ / 2) * size_x_ + x() + size_x_ / 2];
+        const int sx = dev_size_x(), sy = dev_size_y();
+        return __ldg(b200::dev::fld(d_coef_) + (y() + sy / 2) * sx + x() + sx / 2);
 #else
         b200::host_body_called();
 #endif
     }
     HB_HD data_t operator()(const Domain &dom) const {
 #ifdef __CUDA_ARCH__
-        return d_coef_[(dom.y() + size_y_ / 2) * size_x_ + dom.x() + size_x_ / 2];
+        const int sx = dev_size_x(), sy = dev_size_y();
+        return __ldg(b200::dev::fld(d_coef_) + (dom.y() + sy / 2) * sx + dom.x() + sx / 2);
 #else
         (void)dom; b200::host_body_called();
 #endif
     }
     HB_HD data_t operator()(int xf, int yf) const {
 #ifdef __CUDA_ARCH__
-        return d_coef_[(yf + size_y_ / 2) * size_x_ + xf + size_x_ / 2];
+        const int sx = dev_size_x(), sy = dev_size_y();
+        return __ldg(b200::dev::fld(d_coef_) + (yf + sy / 2) * sx + xf + sx / 2);
 #else
         (void)xf; (void)yf; b200::host_body_called();
 #endif
@@ -445,21 +459,29 @@ template <typename data_t> class Accessor : public AccessorBase {
 #ifdef __CUDA_ARCH__
     // image pixel (x, y) through the boundary mode of this accessor's region: pixel_bh of dsl/image.hpp:574-612
     __device__ __forceinline__ data_t &dev_pixel_bh(int x, int y) const {
-        if (bmode == Boundary::CONSTANT) {
-            if (x < offset_x_ || x >= offset_x_ + width_ || y < offset_y_ || y >= offset_y_ + height_) return const_cast<data_t &>(d_const_);
-        } else if (bmode != Boundary::UNDEFINED) {
-            x = b200::dev::remap(x, offset_x_, offset_x_ + width_, bmode);
-            y = b200::dev::remap(y, offset_y_, offset_y_ + height_, bmode);
+        using b200::dev::fld;
+        const int ox = fld(offset_x_), oy = fld(offset_y_), w = fld(width_), h = fld(height_), iw = fld(d_iw_), ih = fld(d_ih_);
+        const Boundary bm = fld(bmode);
+        if (bm == Boundary::CONSTANT) {
+            if (x < ox || x >= ox + w || y < oy || y >= oy + h) return const_cast<data_t &>(d_const_);
+        } else if (bm != Boundary::UNDEFINED) {
+            x = b200::dev::remap(x, ox, ox + w, bm);
+            y = b200::dev::remap(y, oy, oy + h, bm);
         }
-        x = x < 0 ? 0 : x >= d_iw_ ? d_iw_ - 1 : x;   // memory safety for UNDEFINED / degenerate regions
-        y = y < 0 ? 0 : y >= d_ih_ ? d_ih_ - 1 : y;
-        return d_ptr_[(size_t)y * d_stride_ + x];
+        x = x < 0 ? 0 : x >= iw ? iw - 1 : x;   // memory safety for UNDEFINED / degenerate regions
+        y = y < 0 ? 0 : y >= ih ? ih - 1 : y;
+        return fld(d_ptr_)[(size_t)y * fld(d_stride_) + x];
     }
     // the value this thread's pixel sees at tap (dx, dy): plain, or through the interpolation mode (dsl/image.hpp:390-528)
     __device__ __forceinline__ data_t &dev_fetch(int dx, int dy) const {
+        if (b200::dev::fld(imode) == Interpolate::NO)
+            return dev_pixel_bh(b200::dev::fld(offset_x_) + b200::dev::gx() + dx, b200::dev::fld(offset_y_) + b200::dev::gy() + dy);
+        return dev_fetch_interp(dx, dy);
+    }
+    // out of line: the plain path above stays a handful of instructions wherever an accessor call is inlined
+    __device__ __noinline__ data_t &dev_fetch_interp(int dx, int dy) const {
         using hipacc_b200::to_float;
         typedef typename hipacc_b200::float_of<data_t>::type F;
-        if (imode == Interpolate::NO) return dev_pixel_bh(offset_x_ + b200::dev::gx() + dx, offset_y_ + b200::dev::gy() + dy);
         const int *is = b200::dev::is_dims();
         const float stride_x = width_ / (float)is[0], stride_y = height_ / (float)is[1];
         const float x_mapped = offset_x_ + stride_x / 2 + stride_x * (b200::dev::gx() + dx);
@@ -1121,13 +1143,14 @@ template <typename data_t, typename bin_t> class Kernel {
     // dsl/kernel.hpp:241-267: row-major over the mask, the first tap initialises, every later one folds by `mode`
     template <typename data_m, typename F> HB_HD auto convolve(Mask<data_m> &mask, Reduce mode, const F &fun) -> decltype(fun()) {
 #ifdef __CUDA_ARCH__
-        const int sx = mask.size_x(), sy = mask.size_y();
-        mask.dev_seek(-(sx / 2), -(sy / 2));
+        const int hx = mask.dev_size_x() / 2, hy = mask.dev_size_y() / 2;
+        mask.dev_seek(-hx, -hy);
         auto result = fun();
-        for (int k = 1; k < sx * sy; ++k) {
-            mask.dev_seek(k % sx - sx / 2, k / sx - sy / 2);
-            fold_(result, fun(), mode);
-        }
+        for (int dy = -hy; dy <= hy; ++dy)
+            for (int dx = (dy == -hy ? -hx + 1 : -hx); dx <= hx; ++dx) {
+                mask.dev_seek(dx, dy);
+                fold_(result, fun(), mode);
+            }
         return result;
 #else
         (void)mask; (void)mode; (void)fun; b200::host_body_called();
@@ -1136,15 +1159,17 @@ template <typename data_t, typename bin_t> class Kernel {
     // dsl/kernel.hpp:270-296 with the Domain's holes skipped (dsl/mask.hpp:112-126)
     template <typename F> HB_HD auto reduce(Domain &dom, Reduce mode, const F &fun) -> decltype(fun()) {
 #ifdef __CUDA_ARCH__
-        const int sx = dom.size_x(), sy = dom.size_y();
+        const int hx = dom.dev_size_x() / 2, hy = dom.dev_size_y() / 2;
         decltype(fun()) result{};
         bool first = true;
-        for (int k = 0; k < sx * sy; ++k) {
-            if (!dom.dev_visited(k)) continue;
-            dom.dev_seek(k % sx - sx / 2, k / sx - sy / 2);
-            if (first) { result = fun(); first = false; }
-            else fold_(result, fun(), mode);
-        }
+        int k = 0;
+        for (int dy = -hy; dy <= hy; ++dy)
+            for (int dx = -hx; dx <= hx; ++dx, ++k) {
+                if (!dom.dev_visited(k)) continue;
+                dom.dev_seek(dx, dy);
+                if (first) { result = fun(); first = false; }
+                else fold_(result, fun(), mode);
+            }
         return result;
 #else
         (void)dom; (void)mode; (void)fun; b200::host_body_called();
@@ -1152,12 +1177,14 @@ template <typename data_t, typename bin_t> class Kernel {
     }
     template <typename F> HB_HD void iterate(Domain &dom, const F &fun) {
 #ifdef __CUDA_ARCH__
-        const int sx = dom.size_x(), sy = dom.size_y();
-        for (int k = 0; k < sx * sy; ++k) {
-            if (!dom.dev_visited(k)) continue;
-            dom.dev_seek(k % sx - sx / 2, k / sx - sy / 2);
-            fun();
-        }
+        const int hx = dom.dev_size_x() / 2, hy = dom.dev_size_y() / 2;
+        int k = 0;
+        for (int dy = -hy; dy <= hy; ++dy)
+            for (int dx = -hx; dx <= hx; ++dx, ++k) {
+                if (!dom.dev_visited(k)) continue;
+                dom.dev_seek(dx, dy);
+                fun();
+            }
 #else
         (void)dom; (void)fun; b200::host_body_called();
 #endif
