@@ -81,8 +81,10 @@ __device__ __forceinline__ int gx() { return (int)(blockIdx.x * kBlockX + thread
 __device__ __forceinline__ int gy() { return (int)(blockIdx.y * kBlockY + threadIdx.y); }
 // the current offset of a Mask / Domain iteration (convolve / reduce / iterate set it, mask() / in(mask) read it) is
 // per-thread state of an object that all threads share: it lives in shared memory, one cell per (object, thread)
-__device__ __forceinline__ int &iter_state(int slot) {
-    __shared__ int cells[kSlots][kBlockX * kBlockY];
+// (two ints per cell, x and y: a 32-bit store read back by a 32-bit load of the same address is forwarded by the compiler
+// when the tap loop is unrolled, a packed word read back in halves is not)
+__device__ __forceinline__ int2 &iter_state(int slot) {
+    __shared__ int2 cells[kSlots][kBlockX * kBlockY];
     return cells[slot][threadIdx.y * kBlockX + threadIdx.x];
 }
 #endif
@@ -90,12 +92,11 @@ __device__ __forceinline__ int &iter_state(int slot) {
 #ifdef __CUDACC__
 // A device-side field of a snapshot object.  The objects live in the launch's arena in GLOBAL memory and nothing writes
 // them during the kernel, but the compiler only sees a generic `this` that might alias the shared-memory cells of
-// iter_state: without help it reloads every field after every seek.  ld.global.nc says "read-only for this kernel".
+// iter_state: without help it reloads every field after every seek.  __builtin_assume(__isGlobal(p)) tells it the address space: a global load cannot alias a shared-memory store, so the
+// fields are loaded once per pixel.
 template <typename T> __device__ __forceinline__ T fld(const T &f) {
-    if constexpr (sizeof(T) == 4) { const unsigned v = __ldg(reinterpret_cast<const unsigned *>(&f)); T r; memcpy(&r, &v, 4); return r; }
-    else if constexpr (sizeof(T) == 8) { const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long *>(&f)); T r; memcpy(&r, &v, 8); return r; }
-    else if constexpr (sizeof(T) == 1) { const unsigned char v = __ldg(reinterpret_cast<const unsigned char *>(&f)); T r; memcpy(&r, &v, 1); return r; }
-    else return f;
+    __builtin_assume(__isGlobal(&f));   // a plain load the compiler knows to be global: common subexpressions across the taps
+    return f;
 }
 constexpr int kInterpSlots = 4;    // interpolating Accessors one kernel() body may read
 // size of the iteration space (the interpolating accessors scale by it), published by every thread of the CTA
@@ -255,21 +256,21 @@ class MaskBase {
     // offset of the current iteration step relative to the centre (dsl/mask.hpp:100-110)
     HB_HD int x() const {
 #ifdef __CUDA_ARCH__
-        return (short)(b200::dev::iter_state(b200::dev::fld(d_slot_)) & 0xffff);
+        return b200::dev::iter_state(b200::dev::fld(d_slot_)).x;
 #else
         b200::host_body_called();
 #endif
     }
     HB_HD int y() const {
 #ifdef __CUDA_ARCH__
-        return b200::dev::iter_state(b200::dev::fld(d_slot_)) >> 16;
+        return b200::dev::iter_state(b200::dev::fld(d_slot_)).y;
 #else
         b200::host_body_called();
 #endif
     }
-#ifdef __CUDA_ARCH__
-    __device__ __forceinline__ void dev_seek(int dx, int dy) const { b200::dev::iter_state(b200::dev::fld(d_slot_)) = (dy << 16) | (dx & 0xffff); }
-    __device__ __forceinline__ bool dev_visited(int k) const { return __ldg(b200::dev::fld(d_domain_) + k) != 0; }
+#ifdef __CUDACC__
+    __device__ __forceinline__ void dev_seek(int dx, int dy) const { b200::dev::iter_state(b200::dev::fld(d_slot_)) = make_int2(dx, dy); }
+    __device__ __forceinline__ bool dev_visited(int k) const { return b200::dev::fld(b200::dev::fld(d_domain_)[k]) != 0; }
     __device__ __forceinline__ int dev_size_x() const { return b200::dev::fld(size_x_); }
     __device__ __forceinline__ int dev_size_y() const { return b200::dev::fld(size_y_); }
 #endif
@@ -339,7 +340,7 @@ template <typename data_t> class Mask : public MaskBase {
     HB_HD data_t operator()() const {
 #ifdef __CUDA_ARCH__
         const int sx = dev_size_x(), sy = dev_size_y();
-        return __ldg(b200::dev::fld(d_coef_) + (y() + sy / 2) * sx + x() + sx / 2);
+        return b200::dev::fld(b200::dev::fld(d_coef_)[(y() + sy / 2) * sx + x() + sx / 2]);
 #else
         b200::host_body_called();
 #endif
@@ -347,7 +348,7 @@ template <typename data_t> class Mask : public MaskBase {
     HB_HD data_t operator()(const Domain &dom) const {
 #ifdef __CUDA_ARCH__
         const int sx = dev_size_x(), sy = dev_size_y();
-        return __ldg(b200::dev::fld(d_coef_) + (dom.y() + sy / 2) * sx + dom.x() + sx / 2);
+        return b200::dev::fld(b200::dev::fld(d_coef_)[(dom.y() + sy / 2) * sx + dom.x() + sx / 2]);
 #else
         (void)dom; b200::host_body_called();
 #endif
@@ -355,7 +356,7 @@ template <typename data_t> class Mask : public MaskBase {
     HB_HD data_t operator()(int xf, int yf) const {
 #ifdef __CUDA_ARCH__
         const int sx = dev_size_x(), sy = dev_size_y();
-        return __ldg(b200::dev::fld(d_coef_) + (yf + sy / 2) * sx + xf + sx / 2);
+        return b200::dev::fld(b200::dev::fld(d_coef_)[(yf + sy / 2) * sx + xf + sx / 2]);
 #else
         (void)xf; (void)yf; b200::host_body_called();
 #endif
@@ -738,9 +739,12 @@ template <size_t N, size_t A> struct alignas(A) Blob { unsigned char b[N]; };
 template <class K> __global__ void __launch_bounds__(kBlockX *kBlockY) dsl_kernel(const __grid_constant__ Blob<sizeof(K), alignof(K)> blob, int is_w, int is_h) {
     is_dims()[0] = is_w; is_dims()[1] = is_h;   // every thread writes the same two values
     if (gx() >= is_w || gy() >= is_h) return;
-    // the Kernel object as the host built it, references redirected to the device copies of what they point to.  It is
-    // used in place (constant bank): a body that ASSIGNS to a data member of its Kernel is not supported.
-    K &k = *const_cast<K *>(reinterpret_cast<const K *>(blob.b));
+    // the Kernel object as the host built it, references redirected to the device copies of what they point to.  Each
+    // thread works on its own copy: the members (above all the redirected references) then live in registers, which lets
+    // the compiler see that every tap reads the same Accessor / Mask objects
+    alignas(K) unsigned char local[sizeof(K)];
+    memcpy(local, blob.b, sizeof(K));
+    K &k = *reinterpret_cast<K *>(local);
     k.K::kernel();
 }
 
@@ -1140,10 +1144,17 @@ template <typename data_t, typename bin_t> class Kernel {
         b200::host_body_called();
 #endif
     }
-    // dsl/kernel.hpp:241-267: row-major over the mask, the first tap initialises, every later one folds by `mode`
+    // dsl/kernel.hpp:241-267: row-major over the mask, the first tap initialises, every later one folds by `mode`.
+    // The mask's size is a run-time member, but 3x3 / 5x5 / 7x7 cover almost every program: those sizes take a fully unrolled
+    // copy of the loop (a warp-uniform switch), where the tap offsets are constants and the compiler keeps the accessor's and
+    // the mask's fields in registers across the taps -- 4x fewer instructions per tap than the generic loop.
     template <typename data_m, typename F> HB_HD auto convolve(Mask<data_m> &mask, Reduce mode, const F &fun) -> decltype(fun()) {
 #ifdef __CUDA_ARCH__
-        const int hx = mask.dev_size_x() / 2, hy = mask.dev_size_y() / 2;
+        const int sx = mask.dev_size_x(), sy = mask.dev_size_y();
+        if (sx == 3 && sy == 3) return convolve_n_<1, 1>(mask, mode, fun);
+        if (sx == 5 && sy == 5) return convolve_n_<2, 2>(mask, mode, fun);
+        if (sx == 7 && sy == 7) return convolve_n_<3, 3>(mask, mode, fun);
+        const int hx = sx / 2, hy = sy / 2;
         mask.dev_seek(-hx, -hy);
         auto result = fun();
         for (int dy = -hy; dy <= hy; ++dy)
@@ -1159,7 +1170,11 @@ template <typename data_t, typename bin_t> class Kernel {
     // dsl/kernel.hpp:270-296 with the Domain's holes skipped (dsl/mask.hpp:112-126)
     template <typename F> HB_HD auto reduce(Domain &dom, Reduce mode, const F &fun) -> decltype(fun()) {
 #ifdef __CUDA_ARCH__
-        const int hx = dom.dev_size_x() / 2, hy = dom.dev_size_y() / 2;
+        const int sx = dom.dev_size_x(), sy = dom.dev_size_y();
+        if (sx == 3 && sy == 3) return reduce_n_<1, 1>(dom, mode, fun);
+        if (sx == 5 && sy == 5) return reduce_n_<2, 2>(dom, mode, fun);
+        if (sx == 7 && sy == 7) return reduce_n_<3, 3>(dom, mode, fun);
+        const int hx = sx / 2, hy = sy / 2;
         decltype(fun()) result{};
         bool first = true;
         int k = 0;
@@ -1177,7 +1192,11 @@ template <typename data_t, typename bin_t> class Kernel {
     }
     template <typename F> HB_HD void iterate(Domain &dom, const F &fun) {
 #ifdef __CUDA_ARCH__
-        const int hx = dom.dev_size_x() / 2, hy = dom.dev_size_y() / 2;
+        const int sx = dom.dev_size_x(), sy = dom.dev_size_y();
+        if (sx == 3 && sy == 3) return iterate_n_<1, 1>(dom, fun);
+        if (sx == 5 && sy == 5) return iterate_n_<2, 2>(dom, fun);
+        if (sx == 7 && sy == 7) return iterate_n_<3, 3>(dom, fun);
+        const int hx = sx / 2, hy = sy / 2;
         int k = 0;
         for (int dy = -hy; dy <= hy; ++dy)
             for (int dx = -hx; dx <= hx; ++dx, ++k) {
@@ -1191,6 +1210,45 @@ template <typename data_t, typename bin_t> class Kernel {
     }
 
   private:
+#ifdef __CUDACC__
+    template <int HX, int HY, typename data_m, typename F> __device__ __forceinline__ auto convolve_n_(Mask<data_m> &mask, Reduce mode, const F &fun) -> decltype(fun()) {
+        mask.dev_seek(-HX, -HY);
+        auto result = fun();
+#pragma unroll
+        for (int dy = -HY; dy <= HY; ++dy)
+#pragma unroll
+            for (int dx = -HX; dx <= HX; ++dx) {
+                if (dy == -HY && dx == -HX) continue;
+                mask.dev_seek(dx, dy);
+                fold_(result, fun(), mode);
+            }
+        return result;
+    }
+    template <int HX, int HY, typename F> __device__ __forceinline__ auto reduce_n_(Domain &dom, Reduce mode, const F &fun) -> decltype(fun()) {
+        decltype(fun()) result{};
+        bool first = true;
+#pragma unroll
+        for (int dy = -HY; dy <= HY; ++dy)
+#pragma unroll
+            for (int dx = -HX; dx <= HX; ++dx) {
+                if (!dom.dev_visited((dy + HY) * (2 * HX + 1) + dx + HX)) continue;
+                dom.dev_seek(dx, dy);
+                if (first) { result = fun(); first = false; }
+                else fold_(result, fun(), mode);
+            }
+        return result;
+    }
+    template <int HX, int HY, typename F> __device__ __forceinline__ void iterate_n_(Domain &dom, const F &fun) {
+#pragma unroll
+        for (int dy = -HY; dy <= HY; ++dy)
+#pragma unroll
+            for (int dx = -HX; dx <= HX; ++dx) {
+                if (!dom.dev_visited((dy + HY) * (2 * HX + 1) + dx + HX)) continue;
+                dom.dev_seek(dx, dy);
+                fun();
+            }
+    }
+#endif
     template <typename R> HB_HD static void fold_(R &result, const R &v, Reduce mode) {
         switch (mode) {
         case Reduce::SUM: result += v; break;
