@@ -14,6 +14,7 @@
 // rounded float ops like the C++ expression.  Results are bit-identical to the unfused pipeline.
 #include "hb_common.cuh"
 #include "hb_internal.h"
+#include "hb_tma.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -341,6 +342,168 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
     }
 }
 
+
+// ================================================================================================
+// Version 3: the same integer values at every stage as version 2, fewer instructions around them.
+//   stage A  interior tiles: ONE thread requests the 160 x 36 byte box with cp.async.bulk.tensor.2d (SASS: UTMALDG) on an
+//            mbarrier -- no per-thread address arithmetic, loads or shared-memory stores (version 2: ~140 of ~1400
+//            instructions per thread); the co-resident CTAs compute meanwhile.  Border tiles: all threads, through CLAMP.
+//   stage B  as version 2 (five IDP.4A per position, products as packed 16-bit pairs); the xy plane is stored with a bias:
+//            |dx*6| + |dy*6| <= 1020 for any 3x3 byte window (the two sums share their corner pixels), so
+//            |qx * qy| <= 85 * 85 = 7225 and xy + 8192 is an unsigned 14-bit value like xx and yy.
+//   stage C  VERTICAL pass first, on the packed pairs: a + 2b + c of three plane rows is two 32-bit integer operations for
+//            two pixels (every half stays below 2^16: 4 * 16129, 4 * 15417); the horizontal [1 2 1] is then two IDP.2A per
+//            pixel and plane on the 16-bit column sums -- 19 instructions per output row and plane instead of 28.5, and
+//            no accumulators that live across rows (version 2 spilled two of its 48).
+// ================================================================================================
+constexpr int H3_TIN_STRIDE = 160, H3_TIN_ROWS = 37;  // byte (r, t) <-> input (gy0 - 2 + r, gx0 - 16 + t); the TMA box is 160 x 36
+constexpr int H3_PL_COLS = 136, H3_PL_ROWS = 35;      // plane (q, c) <-> intermediate position (jy, jx) = (q - 1, c - 6)
+constexpr int H3_NT = 256;
+constexpr int H3_XY_BIAS = 8192;
+constexpr unsigned H3_BOX_BYTES = 160 * 36;
+
+template <int MINB>
+__global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid_constant__ HarrisParams p, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) unsigned char tin[H3_TIN_ROWS * H3_TIN_STRIDE];
+    __shared__ __align__(16) unsigned short sxx[H3_PL_ROWS * H3_PL_COLS];
+    __shared__ __align__(16) unsigned short syy[H3_PL_ROWS * H3_PL_COLS];
+    __shared__ __align__(16) unsigned short sxy[H3_PL_ROWS * H3_PL_COLS];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int gx0 = blockIdx.x * HTW, gy0 = blockIdx.y * HTH;
+
+    // ---- stage A
+    {
+        const int x_need = p.in_ox + gx0 - 4, y_start = p.in_oy + gy0 - 2;   // image coordinates of (r = 0, t = 12)
+        const bool interior = x_need >= p.win.lo_x && x_need + 136 <= p.win.hi_x && y_start >= p.win.lo_y && y_start + 36 <= p.win.hi_y;
+        if (interior) {
+            if (tid == 0) {
+                mbar_init(&bar, 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(&bar, H3_BOX_BYTES);
+                tma_load_2d(tin, &tmap, x_need - 12, y_start, &bar);   // 16-byte aligned origin (launch condition: in_ox % 16 == 0)
+            }
+            __syncthreads();   // the initialised barrier is visible to the waiting threads
+            mbar_wait(&bar, 0);
+        } else {
+            ImgRef<uchar> im{p.in, p.in_stride, p.in_iw, p.in_ih};
+            for (int e = tid; e < 36 * 136; e += H3_NT) {
+                const int r = e / 136, c = e - r * 136;
+                tin[r * H3_TIN_STRIDE + 12 + c] = fetch_bh(im, p.win, x_need + c, y_start + r, (uchar)0);
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- stage B: group g = intermediate columns jx = 4g - 2 .. 4g + 1 (plane columns 4g + 4 ..), chunk k = plane rows 5k .. 5k + 4
+    if (tid < 33 * 7) {
+        const int g = tid % 33, k = tid / 33;
+        unsigned win[2][4];   // byte windows (a[i-1], a[i], a[i+1], a[i+2]) of the two input rows above
+#pragma unroll
+        for (int rr = 0; rr < 7; ++rr) {
+            const unsigned *row = reinterpret_cast<const unsigned *>(tin + (5 * k + rr) * H3_TIN_STRIDE) + g + 3;   // bytes t = 4g + 12 .. 4g + 19
+            const unsigned w0 = row[0], w1 = row[1];
+            unsigned cur[4] = {__byte_perm(w0, w1, 0x4321), __byte_perm(w0, w1, 0x5432), __byte_perm(w0, w1, 0x6543), w1};
+            if (rr >= 2) {
+                const int q = 5 * k + rr - 2;   // plane row; input rows: win[0] = above, win[1] = centre, cur = below
+                unsigned pxx[4], pyy[4], pxy[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int dx6 = dp4a_us(cur[i], 0x000100FF, dp4a_us(win[1][i], 0x000100FF, dp4a_us(win[0][i], 0x000100FF, 0)));
+                    const int dy6 = dp4a_us(cur[i], 0x00010101, dp4a_us(win[0][i], 0x00FFFFFF, 0));
+                    const int qx = dx6 / 6, qy = dy6 / 6;   // C truncating division (multiply-high by the compiler)
+                    pxx[i] = (unsigned)(qx * qx);
+                    pyy[i] = (unsigned)(qy * qy);
+                    pxy[i] = (unsigned)(qx * qy + H3_XY_BIAS);
+                }
+                const int o = q * H3_PL_COLS + 4 * g + 4;
+                *reinterpret_cast<uint2 *>(sxx + o) = make_uint2(mad_u32(pxx[1], 65536u, pxx[0]), mad_u32(pxx[3], 65536u, pxx[2]));
+                *reinterpret_cast<uint2 *>(syy + o) = make_uint2(mad_u32(pyy[1], 65536u, pyy[0]), mad_u32(pyy[3], 65536u, pyy[2]));
+                *reinterpret_cast<uint2 *>(sxy + o) = make_uint2(mad_u32(pxy[1], 65536u, pxy[0]), mad_u32(pxy[3], 65536u, pxy[2]));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { win[0][i] = win[1][i]; win[1][i] = cur[i]; }
+        }
+    }
+    __syncthreads();
+
+    // ---- fix-up: the Gaussian stage applies CLAMP to the coordinates of the intermediate images
+    {
+        const int ylo = p.win.lo_y - p.in_oy, yhi = p.win.hi_y - p.in_oy;   // intermediates live on [0, w) x [ylo, yhi)
+        if (gx0 == 0 || gx0 + HTW > p.w - 1 || gy0 - 1 < ylo || gy0 + HTH > yhi - 1) {
+            for (int e = tid; e < 34 * 130; e += H3_NT) {
+                const int jy = e / 130 - 1, jx = e - (jy + 1) * 130 - 1;
+                const int X = gx0 + jx, Y = gy0 + jy;
+                const int cx = min(max(X, 0), p.w - 1), cy = min(max(Y, ylo), yhi - 1);
+                if (cx != X || cy != Y) {
+                    const int src = (cy - gy0 + 1) * H3_PL_COLS + (cx - gx0 + 6), dst = (jy + 1) * H3_PL_COLS + (jx + 6);
+                    sxx[dst] = sxx[src]; syy[dst] = syy[src]; sxy[dst] = sxy[src];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- stage C + response: 4 px x 4 rows per thread, one output row at a time over a rolling window of plane rows
+    const int tx = tid & 31, ty = tid >> 5;
+    const int gx = gx0 + 4 * tx, gyb = gy0 + 4 * ty;
+    if (gx >= p.w || gyb >= p.h) return;
+    const int nrows = p.h - gyb;
+    uchar *dst = p.out + (size_t)(p.out_oy + gyb) * p.out_stride + p.out_ox + gx;
+    const bool vec = gx + 3 < p.w && ((reinterpret_cast<uintptr_t>(dst) | (unsigned)p.out_stride) & 3u) == 0;
+    constexpr unsigned cw = 0x00010201u;   // dp2a.lo: (1, 2) on (v[i-1], v[i]); dp2a.hi: (1, 0) on (v[i+1], v[i+2])
+    const int o0 = 4 * ty * H3_PL_COLS + 4 * tx + 4;   // plane columns 4tx + 4 .. 4tx + 11 (8-byte aligned)
+    const unsigned short *pl0 = sxx + o0, *pl1 = syy + o0, *pl2 = sxy + o0;
+    uint2 ra[3][2], rb[3][2];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const unsigned short *pp = pl == 0 ? pl0 : pl == 1 ? pl1 : pl2;
+        ra[pl][0] = *reinterpret_cast<const uint2 *>(pp); ra[pl][1] = *reinterpret_cast<const uint2 *>(pp + 4);
+        rb[pl][0] = *reinterpret_cast<const uint2 *>(pp + H3_PL_COLS); rb[pl][1] = *reinterpret_cast<const uint2 *>(pp + H3_PL_COLS + 4);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r >= nrows) return;   // rows below the image
+        {
+            int G[3][4];
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                const unsigned short *pp = (pl == 0 ? pl0 : pl == 1 ? pl1 : pl2) + (r + 2) * H3_PL_COLS;
+                const uint2 c0 = *reinterpret_cast<const uint2 *>(pp), c1 = *reinterpret_cast<const uint2 *>(pp + 4);
+                // column sums a + 2b + c of the three rows, two pixels per register (no carry between the halves)
+                const unsigned V0 = mad_u32(rb[pl][0].x, 2u, ra[pl][0].x) + c0.x, V1 = mad_u32(rb[pl][0].y, 2u, ra[pl][0].y) + c0.y;
+                const unsigned V2 = mad_u32(rb[pl][1].x, 2u, ra[pl][1].x) + c1.x, V3 = mad_u32(rb[pl][1].y, 2u, ra[pl][1].y) + c1.y;
+                ra[pl][0] = rb[pl][0]; ra[pl][1] = rb[pl][1]; rb[pl][0] = c0; rb[pl][1] = c1;
+                const unsigned p12 = __byte_perm(V0, V1, 0x5432), p34 = __byte_perm(V1, V2, 0x5432), p56 = __byte_perm(V2, V3, 0x5432);
+                const int init = pl == 2 ? -16 * H3_XY_BIAS : 0;
+                G[pl][0] = dp2a_hi_uu(p34, cw, dp2a_lo_uu(p12, cw, init));
+                G[pl][1] = dp2a_hi_uu(V2, cw, dp2a_lo_uu(V1, cw, init));
+                G[pl][2] = dp2a_hi_uu(p56, cw, dp2a_lo_uu(p34, cw, init));
+                G[pl][3] = dp2a_hi_uu(V3, cw, dp2a_lo_uu(V2, cw, init));
+            }
+            unsigned o = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = G[0][i] >> 4, y = G[1][i] >> 4;                           // non-negative: >> 4 == / 16
+                const int xy = abs(G[2][i]) >> 4;                                       // |truncating / 16|: only xy * xy is used
+                const float det = (float)(x * y - xy * xy);
+                const float s = (float)(x + y);
+                const float tr = __fmul_rn(__fmul_rn(p.k, s), s);
+                if (__fadd_rn(det, -tr) > p.threshold) o |= 1u << (8 * i);
+            }
+            if (vec) {
+                *reinterpret_cast<unsigned *>(dst) = o;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (gx + i < p.w) dst[i] = (uchar)(o >> (8 * i));
+            }
+            dst += p.out_stride;
+        }
+    }
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -365,13 +528,26 @@ extern "C" int hb_harris(const hb_harris_desc *d, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     OpScope scope(s, "hb_harris");
     dim3 grid((p.w + HTW - 1) / HTW, (p.h + HTH - 1) / HTH);
-    static int v1 = -1;
-    if (v1 < 0) {
-        const char *e = getenv("HB_HARRIS_V1");   // A/B knob: the first version of the fused kernel
-        v1 = (e && atoi(e)) ? 1 : 0;
+    static int ver = -1;
+    if (ver < 0) {
+        const char *e1 = getenv("HB_HARRIS_V1"), *e = getenv("HB_HARRIS_VERSION");   // A/B knobs: the earlier versions of the fused kernel
+        ver = (e1 && atoi(e1)) ? 1 : (e && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : 3;
     }
-    if (v1) harris_fused_kernel<<<grid, dim3(HBX, HBY), 0, s>>>(p);
-    else harris_fused2_kernel<<<grid, H2_NT, 0, s>>>(p);
+    // version 3 stages interior tiles with TMA: 16-byte aligned base, pitch and box origins, else version 2 (all-threads loader)
+    CUtensorMap tmap;
+    const bool tma_ok = ver == 3 && (p.in_ox % 16 == 0) && make_tile_map(&tmap, p.in, HB_U8, p.in_iw, p.in_ih, p.in_stride, H3_TIN_STRIDE, 36);
+    if (ver == 1) harris_fused_kernel<<<grid, dim3(HBX, HBY), 0, s>>>(p);
+    else if (!tma_ok) harris_fused2_kernel<<<grid, H2_NT, 0, s>>>(p);
+    else {
+        static int minb = -1;
+        if (minb < 0) {
+            const char *e = getenv("HB_HARRIS_CTAS");   // tuning knob: resident CTAs per SM the kernel is compiled for (register cap)
+            minb = e ? atoi(e) : 4;
+        }
+        if (minb == 6) harris_fused3_kernel<6><<<grid, H3_NT, 0, s>>>(p, tmap);
+        else if (minb == 5) harris_fused3_kernel<5><<<grid, H3_NT, 0, s>>>(p, tmap);
+        else harris_fused3_kernel<4><<<grid, H3_NT, 0, s>>>(p, tmap);   // 54 registers, no spills: 507 Gpx/s (5 CTAs: 504, 6 CTAs with spills: 481)
+    }
     g_launches++;
     return scope.finish();
 }
