@@ -587,6 +587,10 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
         if halo is not None:
             halo.check()
         del buf, out
+    if world == 1 and not args.no_e2e:
+        entry["e2e"] = c4_e2e(hb, dev, stream, whole, whole_out, Wc, Hc)
+    if world == 1 and rank == 0 and not args.no_cpu:
+        entry["cpu"] = c4_cpu()
     res["C4_harris_32768x32768"] = entry
     del whole, whole_out
 
@@ -661,6 +665,79 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
             sp.gatherG.check()
     res["C5_pyramid8_16384"] = entry
     return res
+
+
+def c4_e2e(hb, dev, stream, whole, whole_out, Wc, Hc, K=16, reps=3):
+    """C4 end to end with HOST buffers: the 1 GiB uchar image goes host -> HBM in K row strips, the fused Harris kernel runs
+    per strip as soon as the strip and the first rows of the next one have landed, the 1 GiB result goes HBM -> host --
+    three streams, both PCIe directions and the kernels overlap (hb_image_write_region_async / hb_harris /
+    hb_image_read_region_async).  One byte in, one byte out per pixel and nine kernels' worth of work in between: the
+    pipeline shape a host round trip suits, where C2 (1 plane in, 3 planes out, 0.25 ms of kernels) is the worst case."""
+    import ctypes as C
+    import torch
+    L = hb.lib()
+    h_in = torch.empty((Hc, Wc), dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty((Hc, Wc), dtype=torch.uint8, pin_memory=True)
+    for y in range(0, Hc, 4096):
+        h_in[y:y + 4096].copy_(whole[y:y + 4096])
+    want = whole_out.clone()          # the device-resident run's result
+    whole.zero_(); whole_out.zero_()
+    torch.cuda.synchronize()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    bounds = [(Hc * k // K, Hc * (k + 1) // K) for k in range(K)]
+    ev_in = [torch.cuda.Event() for _ in range(K)]
+    ev_k = [torch.cuda.Event() for _ in range(K)]
+    ev_start, ev_done = torch.cuda.Event(), torch.cuda.Event()
+
+    def step():
+        ev_start.record(stream)
+        s_in.wait_event(ev_start)
+        s_out.wait_event(ev_start)
+        for k, (y0, y1) in enumerate(bounds):
+            L.hb_image_write_region_async(C.byref(hb.view(whole, roi=(Wc, y1 - y0, 0, y0))), C.c_void_p(h_in.data_ptr() + y0 * Wc), Wc, hb.stream_ptr(s_in))
+            ev_in[k].record(s_in)
+        for k, (y0, y1) in enumerate(bounds):
+            stream.wait_event(ev_in[min(k + 1, K - 1)])        # the strip below holds this strip's two bottom halo rows
+            hb.harris(whole, dst=whole_out, roi=(Wc, y1 - y0, 0, y0), ghost=(y0, Hc - y1), stream=stream)
+            ev_k[k].record(stream)
+            s_out.wait_event(ev_k[k])
+            L.hb_image_read_region_async(C.byref(hb.view(whole_out, roi=(Wc, y1 - y0, 0, y0))), C.c_void_p(h_out.data_ptr() + y0 * Wc), Wc, hb.stream_ptr(s_out))
+        ev_done.record(s_out)
+        stream.wait_event(ev_done)
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ok = all(torch.equal(h_out[y:y + 4096], want[y:y + 4096].cpu()) for y in range(0, Hc, 4096))
+    assert ok, "C4 e2e leg: host result differs from the device-resident run"
+    return {"Gpx_s": Wc * Hc / (ms * 1e-3) / 1e9, "ms": ms, "h2d_bytes_per_step": Wc * Hc, "d2h_bytes_per_step": Wc * Hc,
+            "api": f"{K} row strips: hb_image_write_region_async -> hb_harris (strip ROI, neighbour rows as ghost rows) -> hb_image_read_region_async on three streams, "
+                   "pinned host buffers; host result compared with the device-resident run"}
+
+
+def c4_cpu(rows=4096, repeats=3):
+    """The CPU arm of C4 on a bounded sample: the sample's nine kernels as specialised -emit-cpu shaped loops
+    (oracle/emit_cpu_fast.cpp::ocf_harris, pinned bit for bit against the generic oracle) on a 32768 x `rows` strip."""
+    import numpy as np
+    from hipacc_b200 import synth
+    from oracle import oracle as O
+    O.set_num_threads(len(os.sched_getaffinity(0)))
+    img = synth.image_np("uint8", 32768, rows, seed=4)
+    out = np.empty_like(img)
+    O.harris_fast(img, out=out)      # warm-up: page faults of the eight intermediate images, OpenMP pool
+    best = float("inf")
+    for _ in range(repeats):
+        t = time.perf_counter()
+        O.harris_fast(img, out=out)
+        best = min(best, time.perf_counter() - t)
+    return {"Gpx_s": img.size / best / 1e9, "cores": O.num_threads(), "kind": "port",
+            "sample": f"32768x{rows} strip of the same synthetic image, nine unfused kernels, g++ -O3 AVX2, OpenMP over rows, best of {repeats}"}
 
 
 def extra_operators(hb, dev, peak, use_graph=True):

@@ -348,9 +348,12 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
 //   stage A  interior tiles: ONE thread requests the 160 x 36 byte box with cp.async.bulk.tensor.2d (SASS: UTMALDG) on an
 //            mbarrier -- no per-thread address arithmetic, loads or shared-memory stores (version 2: ~140 of ~1400
 //            instructions per thread); the co-resident CTAs compute meanwhile.  Border tiles: all threads, through CLAMP.
-//   stage B  as version 2 (five IDP.4A per position, products as packed 16-bit pairs); the xy plane is stored with a bias:
-//            |dx*6| + |dy*6| <= 1020 for any 3x3 byte window (the two sums share their corner pixels), so
-//            |qx * qy| <= 85 * 85 = 7225 and xy + 8192 is an unsigned 14-bit value like xx and yy.
+//   stage B  two IDP.4A per position and input row (D = a[i+1] - a[i-1], S = a[i-1] + a[i] + a[i+1]) kept for three rows:
+//            dx*6 = D0 + D1 + D2 is one three-input add, dy*6 = S2 - S0 one subtraction (version 2: five IDP.4A); products
+//            as packed 16-bit pairs straight from the multiplier -- the odd position's quotients are scaled by 256, so
+//            x1*x1 + x0*x0 IS the packed pair; the xy plane is stored with a bias: |dx*6| + |dy*6| <= 1020 for any 3x3
+//            byte window (the two sums share their corner pixels), so |qx * qy| <= 85 * 85 = 7225 and xy + 8192 is an
+//            unsigned 14-bit value like xx and yy.
 //   stage C  VERTICAL pass first, on the packed pairs: a + 2b + c of three plane rows is two 32-bit integer operations for
 //            two pixels (every half stays below 2^16: 4 * 16129, 4 * 15417); the horizontal [1 2 1] is then two IDP.2A per
 //            pixel and plane on the 16-bit column sums -- 19 instructions per output row and plane instead of 28.5, and
@@ -399,31 +402,40 @@ __global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid
     // ---- stage B: group g = intermediate columns jx = 4g - 2 .. 4g + 1 (plane columns 4g + 4 ..), chunk k = plane rows 5k .. 5k + 4
     if (tid < 33 * 7) {
         const int g = tid % 33, k = tid / 33;
-        unsigned win[2][4];   // byte windows (a[i-1], a[i], a[i+1], a[i+2]) of the two input rows above
+        int D[2][4], Ssum[2][4];   // per-row sums of the two input rows above: D = a[i+1] - a[i-1], S = a[i-1] + a[i] + a[i+1]
 #pragma unroll
         for (int rr = 0; rr < 7; ++rr) {
             const unsigned *row = reinterpret_cast<const unsigned *>(tin + (5 * k + rr) * H3_TIN_STRIDE) + g + 3;   // bytes t = 4g + 12 .. 4g + 19
             const unsigned w0 = row[0], w1 = row[1];
-            unsigned cur[4] = {__byte_perm(w0, w1, 0x4321), __byte_perm(w0, w1, 0x5432), __byte_perm(w0, w1, 0x6543), w1};
+            const unsigned cur[4] = {__byte_perm(w0, w1, 0x4321), __byte_perm(w0, w1, 0x5432), __byte_perm(w0, w1, 0x6543), w1};
+            int Dc[4], Sc[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { Dc[i] = dp4a_us(cur[i], 0x000100FF, 0); Sc[i] = dp4a_us(cur[i], 0x00010101, 0); }
             if (rr >= 2) {
-                const int q = 5 * k + rr - 2;   // plane row; input rows: win[0] = above, win[1] = centre, cur = below
-                unsigned pxx[4], pyy[4], pxy[4];
+                const int q = 5 * k + rr - 2;   // plane row; rows: [0] = above, [1] = centre, c = below
+                int qx[4], qy[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int dx6 = dp4a_us(cur[i], 0x000100FF, dp4a_us(win[1][i], 0x000100FF, dp4a_us(win[0][i], 0x000100FF, 0)));
-                    const int dy6 = dp4a_us(cur[i], 0x00010101, dp4a_us(win[0][i], 0x00FFFFFF, 0));
-                    const int qx = dx6 / 6, qy = dy6 / 6;   // C truncating division (multiply-high by the compiler)
-                    pxx[i] = (unsigned)(qx * qx);
-                    pyy[i] = (unsigned)(qy * qy);
-                    pxy[i] = (unsigned)(qx * qy + H3_XY_BIAS);
+                    const int dx6 = D[0][i] + D[1][i] + Dc[i];
+                    const int dy6 = Sc[i] - Ssum[0][i];
+                    qx[i] = dx6 / 6; qy[i] = dy6 / 6;   // C truncating division (multiply-high by the compiler)
+                }
+                // packed products: the odd position's factors are scaled by 256, so its product lands in the upper half
+                unsigned pk[3][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int x0 = qx[2 * h], y0 = qy[2 * h], x1 = qx[2 * h + 1] << 8, y1 = qy[2 * h + 1] << 8;
+                    pk[0][h] = (unsigned)(x1 * x1 + x0 * x0);
+                    pk[1][h] = (unsigned)(y1 * y1 + y0 * y0);
+                    pk[2][h] = (unsigned)(x1 * y1 + (x0 * y0 + (H3_XY_BIAS * 65537)));
                 }
                 const int o = q * H3_PL_COLS + 4 * g + 4;
-                *reinterpret_cast<uint2 *>(sxx + o) = make_uint2(mad_u32(pxx[1], 65536u, pxx[0]), mad_u32(pxx[3], 65536u, pxx[2]));
-                *reinterpret_cast<uint2 *>(syy + o) = make_uint2(mad_u32(pyy[1], 65536u, pyy[0]), mad_u32(pyy[3], 65536u, pyy[2]));
-                *reinterpret_cast<uint2 *>(sxy + o) = make_uint2(mad_u32(pxy[1], 65536u, pxy[0]), mad_u32(pxy[3], 65536u, pxy[2]));
+                *reinterpret_cast<uint2 *>(sxx + o) = make_uint2(pk[0][0], pk[0][1]);
+                *reinterpret_cast<uint2 *>(syy + o) = make_uint2(pk[1][0], pk[1][1]);
+                *reinterpret_cast<uint2 *>(sxy + o) = make_uint2(pk[2][0], pk[2][1]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { win[0][i] = win[1][i]; win[1][i] = cur[i]; }
+            for (int i = 0; i < 4; ++i) { D[0][i] = D[1][i]; D[1][i] = Dc[i]; Ssum[0][i] = Ssum[1][i]; Ssum[1][i] = Sc[i]; }
         }
     }
     __syncthreads();
@@ -542,11 +554,11 @@ extern "C" int hb_harris(const hb_harris_desc *d, void *stream) {
         static int minb = -1;
         if (minb < 0) {
             const char *e = getenv("HB_HARRIS_CTAS");   // tuning knob: resident CTAs per SM the kernel is compiled for (register cap)
-            minb = e ? atoi(e) : 4;
+            minb = e ? atoi(e) : 5;
         }
         if (minb == 6) harris_fused3_kernel<6><<<grid, H3_NT, 0, s>>>(p, tmap);
-        else if (minb == 5) harris_fused3_kernel<5><<<grid, H3_NT, 0, s>>>(p, tmap);
-        else harris_fused3_kernel<4><<<grid, H3_NT, 0, s>>>(p, tmap);   // 54 registers, no spills: 507 Gpx/s (5 CTAs: 504, 6 CTAs with spills: 481)
+        else if (minb == 4) harris_fused3_kernel<4><<<grid, H3_NT, 0, s>>>(p, tmap);
+        else harris_fused3_kernel<5><<<grid, H3_NT, 0, s>>>(p, tmap);   // 48 registers, no spills: 516 Gpx/s at 32768^2 (4 CTAs: 512; 6 CTAs, 40 registers with spills: 481)
     }
     g_launches++;
     return scope.finish();

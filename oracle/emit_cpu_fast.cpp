@@ -15,6 +15,7 @@
 // Anything this file has no specialisation for returns HB_ERR_UNSUPPORTED and the caller uses emit_cpu.cpp.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <omp.h>
 
@@ -239,6 +240,94 @@ int ocf_local_op(const hb_local_desc *d) {
         if (d->size_x == 7) return local_sum_full<uchar, uchar, 7, 7>(*d, d->coef_f32);
     }
     return HB_ERR_UNSUPPORTED;
+}
+
+// The Harris corner pipeline as -emit-cpu prints it: the sample's NINE kernels (Harris_Corner/src/main.cpp:55-164, 230-305)
+// one after the other over eight full-size intermediate images, each a plain row loop under OpenMP with its constant 3x3
+// mask unrolled, the interior columns without boundary handling (vectorised by the compiler), CLAMP at the image edge.
+//   Sobel (uchar -> short): short sum of Input * {-1,0,1} over the six non-zero taps, / 6
+//   Square1 x 2, Square2 (short -> short), Gaussian x 3 (short -> short): int sum of Input * {1,2,1;2,4,2;1,2,1}, / 16
+//   HarrisCorner (3 x short -> uchar): float R = (x*y - xy*xy) - (k*(x+y))*(x+y); R > threshold
+// in / out: dense or pitched uchar images of w x h pixels.  Returns HB_OK.  Bit-identical to the generic oracle pipeline
+// (tests/test_oracle.py::test_fast_cpu_harris_equals_generic_oracle).
+int ocf_harris(const unsigned char *in, unsigned char *out, int w, int h, int in_stride, int out_stride, float k, float threshold) {
+    if (!in || !out || w <= 0 || h <= 0) return HB_ERR_INVALID;
+    const size_t n = (size_t)w * h;
+    // the eight intermediate images live across calls like the sample's Image objects (allocated once, outside any timed
+    // region; not thread-safe: one caller at a time, which is how the tests and the bench use it)
+    static short *buf = nullptr;
+    static size_t cap = 0;
+    if (cap < 8 * n) {
+        free(buf);
+        buf = static_cast<short *>(malloc(8 * n * sizeof(short)));
+        cap = buf ? 8 * n : 0;
+    }
+    if (!buf) return HB_ERR_INVALID;
+    short *dx = buf, *dy = buf + n, *sx = buf + 2 * n, *sy = buf + 3 * n, *sxy = buf + 4 * n, *gx = buf + 5 * n, *gy = buf + 6 * n, *gxy = buf + 7 * n;
+    auto cl = [](int v, int hi) { return v < 0 ? 0 : (v >= hi ? hi - 1 : v); };
+    // ---- Sobel dx / dy: two kernels
+    for (int which = 0; which < 2; ++which) {
+        short *dst = which == 0 ? dx : dy;
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < h; ++y) {
+            const uchar *r0 = in + (size_t)cl(y - 1, h) * in_stride, *r1 = in + (size_t)y * in_stride, *r2 = in + (size_t)cl(y + 1, h) * in_stride;
+            short *o = dst + (size_t)y * w;
+            auto px = [&](int x, int xm, int xp) -> short {
+                short sum;
+                if (which == 0) sum = (short)((short)((short)((short)((short)(-r0[xm] + r0[xp]) - r1[xm]) + r1[xp]) - r2[xm]) + r2[xp]);
+                else sum = (short)((short)((short)((short)((short)(-r0[xm] - r0[x]) - r0[xp]) + r2[xm]) + r2[x]) + r2[xp]);
+                return (short)(sum / 6);
+            };
+            o[0] = px(0, 0, cl(1, w));
+            if (which == 0) {
+                for (int x = 1; x < w - 1; ++x) o[x] = (short)((short)(-r0[x - 1] + r0[x + 1] - r1[x - 1] + r1[x + 1] - r2[x - 1] + r2[x + 1]) / 6);
+            } else {
+                for (int x = 1; x < w - 1; ++x) o[x] = (short)((short)(-r0[x - 1] - r0[x] - r0[x + 1] + r2[x - 1] + r2[x] + r2[x + 1]) / 6);
+            }
+            if (w > 1) o[w - 1] = px(w - 1, w - 2, w - 1);
+        }
+    }
+    // ---- Square1 (dx), Square1 (dy), Square2 (dx, dy): three kernels
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y) { const short *a = dx + (size_t)y * w; short *o = sx + (size_t)y * w; for (int x = 0; x < w; ++x) o[x] = (short)(a[x] * a[x]); }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y) { const short *a = dy + (size_t)y * w; short *o = sy + (size_t)y * w; for (int x = 0; x < w; ++x) o[x] = (short)(a[x] * a[x]); }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y) { const short *a = dx + (size_t)y * w, *b = dy + (size_t)y * w; short *o = sxy + (size_t)y * w; for (int x = 0; x < w; ++x) o[x] = (short)(a[x] * b[x]); }
+    // ---- Gaussian 3x3 / 16 on the three product images: three kernels
+    const short *srcs[3] = {sx, sy, sxy};
+    short *dsts[3] = {gx, gy, gxy};
+    for (int pl = 0; pl < 3; ++pl) {
+        const short *src = srcs[pl];
+        short *dst = dsts[pl];
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < h; ++y) {
+            const short *r0 = src + (size_t)cl(y - 1, h) * w, *r1 = src + (size_t)y * w, *r2 = src + (size_t)cl(y + 1, h) * w;
+            short *o = dst + (size_t)y * w;
+            auto px = [&](int x, int xm, int xp) -> short {
+                const int sum = r0[xm] + 2 * r0[x] + r0[xp] + 2 * r1[xm] + 4 * r1[x] + 2 * r1[xp] + r2[xm] + 2 * r2[x] + r2[xp];
+                return (short)(sum / 16);
+            };
+            o[0] = px(0, 0, cl(1, w));
+            for (int x = 1; x < w - 1; ++x) {
+                const int sum = r0[x - 1] + 2 * r0[x] + r0[x + 1] + 2 * r1[x - 1] + 4 * r1[x] + 2 * r1[x + 1] + r2[x - 1] + 2 * r2[x] + r2[x + 1];
+                o[x] = (short)(sum / 16);
+            }
+            if (w > 1) o[w - 1] = px(w - 1, w - 2, w - 1);
+        }
+    }
+    // ---- HarrisCorner
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y) {
+        const short *a = gx + (size_t)y * w, *b = gy + (size_t)y * w, *c = gxy + (size_t)y * w;
+        uchar *o = out + (size_t)y * out_stride;
+        for (int x = 0; x < w; ++x) {
+            const int X = a[x], Y = b[x], XY = c[x];
+            const float R = (float)((X * Y) - (XY * XY)) - (k * (float)(X + Y)) * (float)(X + Y);
+            o[x] = R > threshold ? 1 : 0;
+        }
+    }
+    return HB_OK;
 }
 
 int ocf_num_threads(void) { return omp_get_max_threads(); }

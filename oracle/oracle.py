@@ -61,6 +61,7 @@ def fast_lib():
             build()
         _fast = C.CDLL(_FAST_PATH)
         _fast.ocf_local_op.argtypes = [C.POINTER(A.hb_local_desc)]
+        _fast.ocf_harris.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
     return _fast
 
 
@@ -208,6 +209,15 @@ def harris(img, k=M.HARRIS_K, threshold=M.HARRIS_THRESHOLD, return_intermediates
     out = point_op(A.POINT_HARRIS, [gx, gy, gxy], A.U8, p=(k, threshold))
     if return_intermediates:
         return out, gx, gy, gxy
+    return out
+
+
+def harris_fast(img, k=M.HARRIS_K, threshold=M.HARRIS_THRESHOLD, out=None):
+    """The same nine kernels through the specialised CPU loops (emit_cpu_fast.cpp::ocf_harris): the TIMED CPU leg of C4."""
+    assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+    if out is None:
+        out = np.empty(img.shape, dtype=np.uint8)
+    _check(fast_lib().ocf_harris(img.ctypes.data, out.ctypes.data, img.shape[1], img.shape[0], img.strides[0], out.strides[0], k, threshold), "harris_fast")
     return out
 
 

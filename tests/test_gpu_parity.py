@@ -474,6 +474,33 @@ def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
             np.testing.assert_array_equal(to_np(out)[g0:g0 + y1 - y0], full[y0:y1])
 
 
+@pytest.mark.parametrize("ox", [16, 32, 5])
+def test_harris_roi_offsets_take_the_tma_or_the_loader_path(hb, oracle, dev, ox):
+    """ROI accessors: CLAMP applies at the ROI edge (dsl/image.hpp:574-580), so the ROI result equals the pipeline run on
+    the cropped image.  A 16-byte aligned ROI origin keeps the TMA-staged kernel (interior tiles several tiles away from
+    every ROI edge); any other origin takes the all-threads loader of version 2."""
+    img = synth.image_np("uint8", 900, 220, seed=21)
+    W, H, oy = 700, 170, 9
+    d = to_dev(hb, img, dev)
+    out = hb.harris(d, roi=(W, H, ox, oy))
+    np.testing.assert_array_equal(to_np(out)[oy:oy + H, ox:ox + W], oracle.harris(np.ascontiguousarray(img[oy:oy + H, ox:ox + W])))
+
+
+@pytest.mark.parametrize("version", ["1", "2"])
+def test_harris_earlier_kernel_versions_stay_exact(version):
+    """Version 2 of the fused kernel is the fallback for images TMA cannot address (and version 1 an A/B knob): the knob
+    is read once per process, so they run in a child process against the oracle."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np, torch; sys.path.insert(0, %r); import hipacc_b200 as hb; from hipacc_b200 import synth; from oracle import oracle as O; "
+            "hb.init(0); O.emit_lib(); o = O; "
+            "ok = all(np.array_equal(hb.harris(torch.from_numpy(i).cuda()).cpu().numpy(), o.harris(i)) "
+            "for i in (synth.image_np('uint8', 517, 300, seed=3), synth.blocks_np(640, 200, seed=5), synth.image_np('uint8', 7, 5, seed=1))); "
+            "print('HARRIS_OK' if ok else 'HARRIS_DIFF')") % root
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "HB_HARRIS_VERSION": version}, capture_output=True, text=True, timeout=300)
+    assert "HARRIS_OK" in r.stdout, r.stdout + r.stderr
+
+
 # ------------------------------------------------------------------ randomised sweep
 def test_randomised_sweep_gpu_vs_oracle(hb, oracle, dev):
     """Seeded fuzz over shapes (1 px up to several tiles, widths that break every alignment assumption), boundary modes,

@@ -405,6 +405,19 @@ def test_fast_cpu_leg_equals_generic_oracle(oracle, b, shape):
             np.testing.assert_array_equal(o1, o2)
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (7, 1), (2, 2), (37, 61), (130, 257)])
+def test_fast_cpu_harris_equals_generic_oracle(oracle, shape):
+    """The timed CPU leg of C4 (nine specialised kernels, emit_cpu_fast.cpp::ocf_harris) equals the generic oracle pipeline
+    bit for bit: noise (every stage far from trivial), blocks (corners fire), extreme values, pitched rows."""
+    h, w = shape
+    for img in (synth.image_np("uint8", w, h, seed=81), synth.blocks_np(w, h, seed=82), np.full((h, w), 255, np.uint8),
+                (np.indices((h, w)).sum(0) % 2 * 255).astype(np.uint8)):
+        np.testing.assert_array_equal(oracle.harris_fast(img), oracle.harris(img))
+    pitched = np.zeros((h, w + 13), np.uint8)
+    pitched[:, :w] = synth.image_np("uint8", w, h, seed=83)
+    np.testing.assert_array_equal(oracle.harris_fast(pitched[:, :w]), oracle.harris(np.ascontiguousarray(pitched[:, :w])))
+
+
 def test_fast_cpu_leg_refuses_what_it_does_not_specialise(oracle):
     u = synth.image_np("uint8", 40, 30, seed=73)
     with pytest.raises(RuntimeError):
