@@ -14,6 +14,7 @@
 // 0, neighbours through the DSL's default CLAMP, dsl/image.hpp:616-620).
 #include "hb_common.cuh"
 #include "hb_internal.h"
+#include "hb_tma.cuh"
 
 #include <cstdlib>
 #include <cstring>
@@ -205,7 +206,8 @@ template <int S> struct DownSmem {
 // one 128 x 32 fine tile at tile coordinates (bx, by); every thread of the CTA must call it (it synchronises)
 // DOG = false: blur + subsample only (lap is not written; the DifferenceOfGaussian runs as its own kernel, pyr_dog_half_kernel)
 template <int S, bool COHERENT, bool DOG = true>
-__device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int bx, const int by, float *ftile, float *ctile) {
+__device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int bx, const int by, float *ftile, float *ctile,
+                                              const CUtensorMap *tmap = nullptr, uint64_t *bar = nullptr) {
     constexpr int H = S / 2;
     constexpr int FROWS = DownSmem<S>::FROWS;
     const int tid = threadIdx.x;
@@ -219,7 +221,18 @@ __device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int
         constexpr int VPR = FD_FCOLS / 4;
         constexpr int NV = FROWS * VPR, PER = (NV + FD_NT - 1) / FD_NT;
         const int xs = X0 - 4, ys = Y0 - 1 - H;
-        if (xs >= 0 && xs + FD_FCOLS <= p.fw) {
+        if (!COHERENT && tmap && xs >= 0 && xs + FD_FCOLS <= p.fw && ys >= -p.fgt && ys + FROWS - 1 <= p.fh - 1 + p.fgb) {
+            // interior tile (no row of the box needs the CLAMP): one thread requests the 144 x FROWS box with
+            // cp.async.bulk.tensor.2d; the map starts at the first ghost row, hence the row coordinate ys + fgt
+            if (tid == 0) {
+                mbar_init(bar, 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(bar, FROWS * FD_FCOLS * (unsigned)sizeof(float));
+                tma_load_2d(ftile, tmap, xs, ys + p.fgt, bar);
+            }
+            __syncthreads();   // the initialised barrier is visible to the waiting threads
+            mbar_wait(bar, 0);
+        } else if (xs >= 0 && xs + FD_FCOLS <= p.fw) {
             float4 t[PER];
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
@@ -349,13 +362,16 @@ __device__ __forceinline__ void pyr_down_tile(const PyrFusedParams &p, const int
     }
 }
 
-template <int S, bool DOG>
-#ifndef HB_PYR_MINB
-#define HB_PYR_MINB 5   // 48 registers, 5 CTAs per SM: 492 vs 513 us at level 0 of the 16384^2 pyramid (4: 64 registers; 6: spills, 526 us)
-#endif
-__global__ void __launch_bounds__(FD_NT, HB_PYR_MINB) pyr_down_fused_kernel(const __grid_constant__ PyrFusedParams p) {
-    __shared__ __align__(16) float smem[DownSmem<S>::FLOATS];
-    pyr_down_tile<S, false, DOG>(p, blockIdx.x, blockIdx.y, smem, smem + DownSmem<S>::FROWS * FD_FCOLS);
+// MINB = resident CTAs per SM the kernel is compiled for.  All-threads staging keeps six 16-byte loads per thread in flight:
+// 48 registers, 5 CTAs (492 vs 513 us at level 0 of the 16384^2 pyramid; 4: 64 registers; 6: spills, 526 us).  With TMA staging
+// those registers are free on the interior tiles: 40 registers, 6 CTAs, 432 us (5 CTAs: 455 us; the spills sit in the border
+// tiles' loader).
+template <int S, bool DOG, int MINB>
+__global__ void __launch_bounds__(FD_NT, MINB) pyr_down_fused_kernel(const __grid_constant__ PyrFusedParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                            const int use_tma) {
+    __shared__ __align__(128) float smem[DownSmem<S>::FLOATS];
+    __shared__ __align__(8) uint64_t bar;
+    pyr_down_tile<S, false, DOG>(p, blockIdx.x, blockIdx.y, smem, smem + DownSmem<S>::FROWS * FD_FCOLS, use_tma ? &tmap : nullptr, &bar);
 }
 
 struct PyrUpHalfParams {
@@ -608,15 +624,24 @@ extern "C" int hb_pyr_down(const hb_pyr_down_desc *d, void *stream) {
             for (int k = 0; k < d->size * d->size; ++k) p.coef[k] = d->coef_f32[k];
             OpScope scope(s, dog ? "hb_pyr_down(fused blur+subsample+DoG)" : "hb_pyr_down(fused blur+subsample)");
             dim3 grid((p.fw + FD_TW - 1) / FD_TW, (p.fh + FD_TH - 1) / FD_TH);
+            // interior tiles are staged by TMA (one request per CTA); the tensor map starts at the first ghost row
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            static int no_tma = -1;
+            if (no_tma < 0) { const char *e = getenv("HB_PYR_NO_TMA"); no_tma = (e && atoi(e)) ? 1 : 0; }   // A/B knob
+            const int frows = 35 + 2 * (d->size / 2);
+            const int use_tma = !no_tma && make_tile_map(&tmap, p.fine - (ptrdiff_t)p.fgt * p.fine_stride, HB_F32, p.fw, p.fh + p.fgt + p.fgb, p.fine_stride, FD_FCOLS, frows);
+#define HB_PD(S_, DOG_) (use_tma ? pyr_down_fused_kernel<S_, DOG_, 6><<<grid, FD_NT, 0, s>>>(p, tmap, 1) : pyr_down_fused_kernel<S_, DOG_, 5><<<grid, FD_NT, 0, s>>>(p, tmap, 0))
             if (dog) {
-                if (d->size == 3) pyr_down_fused_kernel<3, true><<<grid, FD_NT, 0, s>>>(p);
-                else if (d->size == 5) pyr_down_fused_kernel<5, true><<<grid, FD_NT, 0, s>>>(p);
-                else pyr_down_fused_kernel<7, true><<<grid, FD_NT, 0, s>>>(p);
+                if (d->size == 3) HB_PD(3, true);
+                else if (d->size == 5) HB_PD(5, true);
+                else HB_PD(7, true);
             } else {
-                if (d->size == 3) pyr_down_fused_kernel<3, false><<<grid, FD_NT, 0, s>>>(p);
-                else if (d->size == 5) pyr_down_fused_kernel<5, false><<<grid, FD_NT, 0, s>>>(p);
-                else pyr_down_fused_kernel<7, false><<<grid, FD_NT, 0, s>>>(p);
+                if (d->size == 3) HB_PD(3, false);
+                else if (d->size == 5) HB_PD(5, false);
+                else HB_PD(7, false);
             }
+#undef HB_PD
             g_launches++;
             return scope.finish();
         }

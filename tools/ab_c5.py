@@ -30,7 +30,9 @@ if os.environ.get("AB_CHILD"):
         return e0.elapsed_time(e1) / (3 * reps) * 1e3
     t_down = timeit(lambda: hb.pyr_down(img, g1, M.GAUSS5, lap_fine=l0, stream=st), 5)
     t_trav = timeit(lambda: hb.pyramid_traverse(pg, pl, M.GAUSS5, stream=st), 3)
-    print(f"{os.path.basename(hb.LIB_PATH):22s} down L0 {t_down:8.1f} us   traversal {t_trav:8.1f} us = {n * n / t_trav / 1e3:6.1f} Gpx/s", flush=True)
+    print(f"{os.path.basename(hb.LIB_PATH):22s} {os.environ.get('AB_TAG', ''):10s} down L0 {t_down:8.1f} us   traversal {t_trav:8.1f} us = {n * n / t_trav / 1e3:6.1f} Gpx/s", flush=True)
 else:
-    for lib in sys.argv[1:]:
-        subprocess.run([sys.executable, __file__], env={**os.environ, "AB_CHILD": "1", "HIPACC_B200_LIB": os.path.abspath(lib)})
+    # every library is run with and without TMA staging of the fused down step (HB_PYR_NO_TMA, read once per process)
+    for lib in (sys.argv[1:] or [os.path.join(ROOT, "hipacc_b200", "lib", "libhipacc_b200.so")]):
+        for tag, env in (("tma", {}), ("no-tma", {"HB_PYR_NO_TMA": "1"})):
+            subprocess.run([sys.executable, __file__], env={**os.environ, **env, "AB_CHILD": "1", "AB_TAG": tag, "HIPACC_B200_LIB": os.path.abspath(lib)})
