@@ -29,6 +29,8 @@ struct BinParams {
 
 constexpr int HT = 256, HU = 4;
 
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 template <typename T> struct BinVec;
 template <> struct BinVec<float> { typedef float4 V; static constexpr int N = 4; };
 template <> struct BinVec<uchar> { typedef uint4 V; static constexpr int N = 16; };
@@ -68,6 +70,42 @@ __device__ __forceinline__ bool scaled_index(const BinParams &p, float a, unsign
     return f2bin(v, p.nbf, idx);
 }
 
+// Shared-memory path: every pixel issues exactly ONE red.shared.add and no branch.  A pixel that falls into no bin
+// (v <= -1, v >= num_bins, +-inf, NaN) adds to a spare word behind the copy's bins (index num_bins) that the final fold
+// ignores.  The |a| < 1e30 guard of scaled_index() is not needed here: such a pixel's quotient is >= 1e15 in magnitude,
+// inf or NaN, all of which land in the spare word anyway.
+__device__ __forceinline__ unsigned f2bin_spare(float v, float nbf) {
+    float w = v > -1.0f ? v : nbf;            // v <= -1 and NaN -> spare
+    w = fminf(fmaxf(w, 0.0f), nbf);           // (-1, 0) -> bin 0 like the C conversion; v >= num_bins, +inf -> spare
+    return (unsigned)__float_as_int(__fadd_rz(w, 8388608.0f));   // 0x4B000000 + index: the caller's base address carries -4 * 0x4B000000
+}
+constexpr unsigned kF2BinBias = 0x4B000000u;
+template <bool FASTDIV>
+__device__ __forceinline__ unsigned scaled_index_spare(const BinParams &p, float a) {
+    float q;
+    if (FASTDIV) {
+        const float q0 = __fmul_rn(a, p.rp0);
+        q = __fmaf_rn(__fmaf_rn(-p.p0, q0, a), p.rp0, q0);
+    } else {
+        q = __fdiv_rn(a, p.p0);
+    }
+    return f2bin_spare(__fmul_rn(q, p.nbf), p.nbf);
+}
+// sh32 = shared-space byte address of the warp's copy of the bins
+template <typename T, int INDEX, int VALUE, bool FASTDIV>
+__device__ __forceinline__ void bin_put_shared(const BinParams &p, unsigned sh32, T e) {
+    unsigned addr;   // 32-bit arithmetic wraps: (sh32 - 4 * bias) + 4 * (bias + index) = sh32 + 4 * index
+    if (INDEX == HB_BIN_INDEX_SCALE) addr = (sh32 - 4u * kF2BinBias) + 4u * scaled_index_spare<FASTDIV>(p, (float)e);
+    else if (DtypeOf<T>::v == HB_F32) addr = (sh32 - 4u * kF2BinBias) + 4u * f2bin_spare((float)e, p.nbf);
+    else addr = sh32 + 4u * min((unsigned)e, (unsigned)p.num_bins);
+    if (VALUE == HB_BIN_VALUE_ONE) {
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    } else {
+        const unsigned val = DtypeOf<T>::v == HB_F32 ? __float2uint_rz((float)e) : (unsigned)e;
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(val) : "memory");
+    }
+}
+
 template <typename T, int INDEX, int VALUE, bool FASTDIV>
 __device__ __forceinline__ void bin_put(const BinParams &p, unsigned *sh, T e) {
     unsigned idx;
@@ -86,14 +124,21 @@ __device__ __forceinline__ void bin_put(const BinParams &p, unsigned *sh, T e) {
     if (ok) atomicAdd(dst, val);
 }
 
-template <typename T, int INDEX, int VALUE, bool FASTDIV>
+template <typename T, int INDEX, int VALUE, bool FASTDIV, bool SH>
 __global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ BinParams p) {
     typedef typename BinVec<T>::V V;
     constexpr int N = BinVec<T>::N;
     extern __shared__ unsigned hsh[];
-    for (int i = threadIdx.x; i < p.copies * p.num_bins; i += HT) hsh[i] = 0u;
-    __syncthreads();
-    unsigned *my = p.copies ? hsh + ((threadIdx.x >> 5) % p.copies) * p.num_bins : nullptr;
+    const int bstride = p.num_bins + 1;   // the bins of one copy + its spare word
+    if (SH) {
+        for (int i = threadIdx.x; i < p.copies * bstride; i += HT) hsh[i] = 0u;
+        __syncthreads();
+    }
+    const unsigned my32 = SH ? smem_addr(hsh + ((threadIdx.x >> 5) % p.copies) * bstride) : 0u;
+    auto put = [&](T e) {
+        if (SH) bin_put_shared<T, INDEX, VALUE, FASTDIV>(p, my32, e);
+        else bin_put<T, INDEX, VALUE, FASTDIV>(p, nullptr, e);
+    };
 
     const T *in = static_cast<const T *>(p.in);
     const uintptr_t base_addr = reinterpret_cast<uintptr_t>(in) + (size_t)p.ox * sizeof(T);
@@ -119,18 +164,18 @@ __global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ Bin
                 T e[N];
                 unpack(v[k], e);
 #pragma unroll
-                for (int i = 0; i < N; ++i) bin_put<T, INDEX, VALUE, FASTDIV>(p, my, e[i]);
+                for (int i = 0; i < N; ++i) put(e[i]);
             }
         if (c == 0) {  // scalar head / tail pixels of this row
             const int nscal = head_n + (p.w - tail0);
-            for (int k = threadIdx.x; k < nscal; k += HT) bin_put<T, INDEX, VALUE, FASTDIV>(p, my, row[k < head_n ? k : tail0 + (k - head_n)]);
+            for (int k = threadIdx.x; k < nscal; k += HT) put(row[k < head_n ? k : tail0 + (k - head_n)]);
         }
     }
-    if (p.copies) {
+    if (SH) {
         __syncthreads();
         for (int i = threadIdx.x; i < p.num_bins; i += HT) {
             unsigned a = 0;
-            for (int k = 0; k < p.copies; ++k) a += hsh[k * p.num_bins + i];
+            for (int k = 0; k < p.copies; ++k) a += hsh[k * bstride + i];
             if (a) atomicAdd(p.bins + i, a);
         }
     }
@@ -138,8 +183,13 @@ __global__ void __launch_bounds__(HT) binning_kernel(const __grid_constant__ Bin
 
 template <typename T, int INDEX, int VALUE>
 static void launch_binning_kernel(const BinParams &p, bool fastdiv, int blocks, size_t smem, cudaStream_t s) {
-    if (INDEX == HB_BIN_INDEX_SCALE && fastdiv) binning_kernel<T, INDEX, VALUE, true><<<blocks, HT, smem, s>>>(p);
-    else binning_kernel<T, INDEX, VALUE, false><<<blocks, HT, smem, s>>>(p);
+    if (p.copies) {
+        if (INDEX == HB_BIN_INDEX_SCALE && fastdiv) binning_kernel<T, INDEX, VALUE, true, true><<<blocks, HT, smem, s>>>(p);
+        else binning_kernel<T, INDEX, VALUE, false, true><<<blocks, HT, smem, s>>>(p);
+    } else {   // more bins than shared memory holds: global atomics
+        if (INDEX == HB_BIN_INDEX_SCALE && fastdiv) binning_kernel<T, INDEX, VALUE, true, false><<<blocks, HT, 0, s>>>(p);
+        else binning_kernel<T, INDEX, VALUE, false, false><<<blocks, HT, 0, s>>>(p);
+    }
 }
 template <typename T>
 static void dispatch_binning(const BinParams &p, bool fastdiv, int blocks, size_t smem, cudaStream_t s) {
@@ -180,8 +230,9 @@ static int launch_binning(const hb_binning_desc *d, unsigned *bins_dev, cudaStre
         p.rp0 = fastdiv ? 1.0f / b : 0.0f;
     }
     const int max_words = 48 * 1024 / 4;
-    p.copies = d->num_bins > max_words ? 0 : (max_words / d->num_bins < HT / 32 ? max_words / d->num_bins : HT / 32);
-    const size_t smem = (size_t)p.copies * d->num_bins * sizeof(unsigned);
+    const int per_copy = d->num_bins + 1;   // + the spare word that takes the pixels of no bin
+    p.copies = per_copy > max_words ? 0 : (max_words / per_copy < HT / 32 ? max_words / per_copy : HT / 32);
+    const size_t smem = (size_t)p.copies * per_copy * sizeof(unsigned);
     const int npv = v.dtype == HB_F32 ? 4 : 16;
     const long long cpr = (v.width / npv + HT * HU - 1) / (HT * HU);
     const long long chunks = (cpr < 1 ? 1 : cpr) * v.height;

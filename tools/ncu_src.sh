@@ -2,7 +2,7 @@
 # Full ncu capture WITH the source page exported (per-line instruction / stall counters) for the issue-bound kernels.
 # gpurun --timeout 1500 -- 'bash tools/ncu_src.sh <tag> "<kernel regex>|<kernel regex>..."'
 TAG=${1:-r2}
-RE=${2:-local_tiled_kernel|harris_fused2}
+RE=${2:-local_tiled_kernel|harris_fused3}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1

@@ -20,7 +20,7 @@ capture() {  # kernel regex, launches to skip, tag, source page?
 }
 capture local_tma_f32_kernel 3 local_tma
 capture local_pair_kernel 3 local_pair src
-capture harris_fused2 1 harris_fused2 src
+capture harris_fused3 1 harris_fused3 src
 capture pyr_down_fused 0 pyr_down_fused_L0
 capture pyr_up_half 6 pyr_up_half_L0
 capture reduce_mms 2 reduce_mms
