@@ -42,6 +42,7 @@ def lib():
         L.hb_bilateral.argtypes = [C.POINTER(A.hb_bilateral_desc), C.c_void_p]
         L.hb_point_op.argtypes = [C.POINTER(A.hb_point_desc), C.c_void_p]
         L.hb_reduce.argtypes = [C.POINTER(A.hb_view), C.c_int, C.c_void_p, C.c_void_p]
+        L.hb_reduce_async.argtypes = [C.POINTER(A.hb_view), C.c_int, C.c_void_p, C.c_void_p]
         L.hb_reduce_minmaxsum_f32.argtypes = [C.POINTER(A.hb_view), C.POINTER(C.c_float), C.c_void_p]
         L.hb_reduce_minmaxsum_f32_async.argtypes = [C.POINTER(A.hb_view), C.c_void_p, C.c_void_p]
         L.hb_binning.argtypes = [C.POINTER(A.hb_binning_desc), C.c_void_p, C.c_void_p]
@@ -269,6 +270,15 @@ def reduce(src, mode, roi=None, stream=None):
     res = np.zeros(1, dtype=A.DTYPE_NUMPY[v.dtype])
     _check(lib().hb_reduce(C.byref(v), mode, res.ctypes.data_as(C.c_void_p), stream_ptr(stream)), "hb_reduce")
     return res[0]
+
+
+def reduce_async(src, mode, out, roi=None, stream=None):
+    """hb_reduce_async: integer images (every mode) / float PROD; the scalar is left in `out` (a CUDA tensor of >= 8
+    bytes: int32 accumulator for integer pixels, float64 for float PROD).  Capturable."""
+    assert out.is_cuda and out.numel() * out.element_size() >= 8 and out.data_ptr() % 8 == 0
+    v = view(src, roi)
+    _check(lib().hb_reduce_async(C.byref(v), mode, C.c_void_p(out.data_ptr()), stream_ptr(stream)), "hb_reduce_async")
+    return out
 
 
 def _binning_desc(src, num_bins, index_kind, value_kind, p0, roi):

@@ -161,7 +161,7 @@ EXPORTS = [
     "hb_image_copy", "hb_image_copy_region", "hb_image_write_region_async", "hb_image_read_region_async", "hb_set_timing", "hb_last_kernel_ms", "hb_launch_count",
     "hb_stream_synchronize", "hb_debug_timestamp", "hb_stream_create", "hb_stream_destroy", "hb_graph_begin", "hb_graph_end", "hb_graph_launch", "hb_graph_destroy",
     "hb_local_op", "hb_bilateral", "hb_point_op",
-    "hb_reduce", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
+    "hb_reduce", "hb_reduce_async", "hb_reduce_minmaxsum_f32", "hb_reduce_minmaxsum_f32_async",
     "hb_binning", "hb_binning_async",
     "hb_harris", "hb_pyr_down", "hb_pyr_up", "hb_pyr_dog", "hb_pyr_traverse_coarse",
     "hb_ipc_export", "hb_ipc_open", "hb_ipc_close", "hb_halo_ctrl_create", "hb_halo_ctrl_destroy", "hb_halo_status", "hb_halo_exchange", "hb_halo_exchange_batch", "hb_allgather_rows",

@@ -374,6 +374,26 @@ static void launch_int(const ReduceParams &p, int blocks, cudaStream_t s) {
     }
 }
 
+// integer images (any mode) and float PROD: one launch, the scalar is left at `result_dev` (32-bit accumulator for integer
+// pixels, double for float PROD)
+static int launch_generic(const hb_view &v, int mode, void *result_dev, Scratch *sc, cudaStream_t s, const char *who) {
+    HB_REQUIRE(!is_x4(v.dtype), HB_ERR_UNSUPPORTED, "%s: vector pixels have no device reduction; no CPU fallback", who);
+    const int blocks = grid_for(v, dtype_size(v.dtype));
+    ReduceParams p{v.data, v.stride, v.width, v.height, v.offset_x, v.offset_y, sc->partials, sc->ticket, result_dev, mode};
+    switch (v.dtype) {
+    case HB_U8: launch_int<uchar>(p, blocks, s); break;
+    case HB_S8: launch_int<signed char>(p, blocks, s); break;
+    case HB_S16: launch_int<short>(p, blocks, s); break;
+    case HB_U16: launch_int<unsigned short>(p, blocks, s); break;
+    case HB_S32: launch_int<int>(p, blocks, s); break;
+    case HB_U32: launch_int<unsigned int>(p, blocks, s); break;
+    case HB_F32: reduce_prod_f32_kernel<<<blocks, RT, 0, s>>>(p); break;
+    default: log_msg(2, "%s: dtype %d unsupported", who, v.dtype); return HB_ERR_UNSUPPORTED;
+    }
+    g_launches++;
+    return HB_OK;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -425,25 +445,13 @@ extern "C" int hb_reduce(const hb_view *in_, int mode, void *result_host, void *
         *static_cast<float *>(result_host) = mode == HB_REDUCE_MIN ? r[0] : mode == HB_REDUCE_MAX ? r[1] : r[2];
         return rc;
     }
-    HB_REQUIRE(!stream_is_capturing(s), HB_ERR_INVALID, "hb_reduce blocks and cannot be captured");
-    HB_REQUIRE(!is_x4(v.dtype), HB_ERR_UNSUPPORTED, "hb_reduce: vector pixels have no device reduction; no CPU fallback");
+    HB_REQUIRE(!stream_is_capturing(s), HB_ERR_INVALID, "hb_reduce blocks and cannot be captured; use hb_reduce_async");
     Scratch *sc = nullptr;
     int rc = get_scratch(&sc, s);
     if (rc) return rc;
-    const int blocks = grid_for(v, dtype_size(v.dtype));
-    ReduceParams p{v.data, v.stride, v.width, v.height, v.offset_x, v.offset_y, sc->partials, sc->ticket, sc->result, mode};
     OpScope scope(s, "hb_reduce");
-    switch (v.dtype) {
-    case HB_U8: launch_int<uchar>(p, blocks, s); break;
-    case HB_S8: launch_int<signed char>(p, blocks, s); break;
-    case HB_S16: launch_int<short>(p, blocks, s); break;
-    case HB_U16: launch_int<unsigned short>(p, blocks, s); break;
-    case HB_S32: launch_int<int>(p, blocks, s); break;
-    case HB_U32: launch_int<unsigned int>(p, blocks, s); break;
-    case HB_F32: reduce_prod_f32_kernel<<<blocks, RT, 0, s>>>(p); break;
-    default: log_msg(2, "hb_reduce: dtype %d unsupported", v.dtype); return HB_ERR_UNSUPPORTED;
-    }
-    g_launches++;
+    rc = launch_generic(v, mode, sc->result, sc, s, "hb_reduce");
+    if (rc) return rc;
     rc = scope.finish();
     rc |= check_cuda(cudaMemcpyAsync(sc->host, sc->result, sizeof(MMS), cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(result)");
     rc |= check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize()");
@@ -458,4 +466,21 @@ extern "C" int hb_reduce(const hb_view *in_, int mode, void *result_host, void *
     default: *static_cast<float *>(result_host) = (float)*reinterpret_cast<const double *>(sc->host); break;
     }
     return rc ? HB_ERR_CUDA : HB_OK;
+}
+
+extern "C" int hb_reduce_async(const hb_view *in_, int mode, void *result_device, void *stream) {
+    HB_REQUIRE(in_ && result_device, HB_ERR_INVALID, "hb_reduce_async: null argument");
+    HB_REQUIRE(mode >= HB_REDUCE_SUM && mode <= HB_REDUCE_PROD, HB_ERR_INVALID, "hb_reduce_async: bad mode");
+    hb_view v = norm_view(*in_);
+    HB_REQUIRE(view_ok(v), HB_ERR_INVALID, "hb_reduce_async: malformed view");
+    HB_REQUIRE(!(v.dtype == HB_F32 && mode != HB_REDUCE_PROD), HB_ERR_UNSUPPORTED,
+               "hb_reduce_async: float MIN / MAX / SUM come fused from hb_reduce_minmaxsum_f32_async");
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch *sc = nullptr;
+    int rc = get_scratch(&sc, s);
+    if (rc) return rc;
+    OpScope scope(s, "hb_reduce_async");
+    rc = launch_generic(v, mode, result_device, sc, s, "hb_reduce_async");
+    if (rc) return rc;
+    return scope.finish();
 }

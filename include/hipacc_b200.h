@@ -267,6 +267,11 @@ int hb_reduce_minmaxsum_f32(const hb_view *in, float result_host[3], void *strea
 /* asynchronous form for multi-GPU: partial (min,max) as float and sum as double are left in
  * device memory ({float min, float max, double sum}, 16 bytes) for an NCCL all-reduce */
 int hb_reduce_minmaxsum_f32_async(const hb_view *in, void *partials_device, void *stream);
+/* asynchronous (capturable) form of hb_reduce for integer images (every mode) and float PROD: the scalar stays in device
+ * memory at result_device (8 bytes, 8-byte aligned) -- a 32-bit accumulator for integer pixels (the C result is its
+ * truncation to the pixel type, as hb_reduce returns it), a double for float PROD.  Float MIN / MAX / SUM come fused from
+ * hb_reduce_minmaxsum_f32_async.  One reduction in flight per stream (per-stream scratch). */
+int hb_reduce_async(const hb_view *in, int reduce_mode, void *result_device, void *stream);
 
 /* ------------------------------------------------------------------ binning (histograms) */
 /*

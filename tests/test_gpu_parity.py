@@ -435,6 +435,40 @@ def test_first_tap_initialises_and_holes_skip_non_finite_pixels(hb, oracle, dev)
             np.testing.assert_array_equal(got, want)
 
 
+def test_reduce_async_leaves_the_scalar_on_the_device_and_replays_in_a_graph(hb, oracle, dev):
+    """hb_reduce_async (integer images, every mode; float PROD): same scalar as the blocking call, capturable."""
+    import torch
+    rng = np.random.default_rng(77)
+    out = torch.zeros(2, dtype=torch.int32, device=dev)
+    for dt, lo, hi in (("int32", -1000, 1000), ("uint8", 0, 256), ("int16", -300, 300)):
+        a = rng.integers(lo, hi, size=(157, 333)).astype(dt)
+        d = to_dev(hb, a, dev)
+        for mode, want in ((A.SUM, a.astype(np.int64).sum()), (A.MIN, a.min()), (A.MAX, a.max())):
+            hb.reduce_async(d, mode, out)
+            got = int(out[0].item())
+            blocking = hb.reduce(d, mode)
+            assert np.array(got).astype(dt) == np.array(want).astype(dt) == blocking, (dt, mode, got, want, blocking)
+    d = to_dev(hb, rng.integers(-5, 6, size=(300, 500)).astype("int32"), dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        hb.reduce_async(d, A.SUM, out, stream=stream)
+        torch.cuda.synchronize()
+        with hb.Graph(stream) as g:
+            hb.reduce_async(d, A.SUM, out, stream=stream)
+        for k in range(3):
+            d.fill_(k + 1)
+            g.launch()
+            torch.cuda.synchronize()
+            assert int(out[0].item()) == (k + 1) * 300 * 500
+        g.destroy()
+    f = to_dev(hb, (1.0 + rng.random((40, 50)) * 1e-3).astype("float32"), dev)
+    outf = torch.zeros(1, dtype=torch.float64, device=dev)
+    hb.reduce_async(f, A.PROD, outf)
+    assert abs(float(outf.item()) / float(hb.reduce(f, A.PROD)) - 1) < 1e-5
+    with pytest.raises(RuntimeError):
+        hb.reduce_async(f, A.SUM, outf)     # float SUM / MIN / MAX: the fused hb_reduce_minmaxsum_f32_async
+
+
 # ------------------------------------------------------------------ Harris
 @pytest.mark.parametrize("shape", [cases.HARRIS_SHAPE, (200, 333), (33, 129), (5, 7)])
 def test_harris_fused_and_unfused(hb, oracle, dev, shape):
