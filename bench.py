@@ -568,6 +568,9 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
         out = torch.zeros_like(buf)
         halo = strips.P2PHalo(hb, buf, plan) if p2p else None
 
+        # The exchange runs in stream order ahead of the fused kernel.  Overlapping it with the interior rows (halo kernel on a
+        # side stream, two 32-row edge bands after the join -- what the C2 step does) was measured SLOWER here: 305 vs 295 us per
+        # step at N = 8 (profiles/r4n_bench_n8_c4overlap.json): two extra launches of 256 CTAs cost more than the ~10 us exchange.
         def harris_step():
             if halo is not None:
                 halo.exchange(stream)
