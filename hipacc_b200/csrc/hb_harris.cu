@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
 //            unsigned 14-bit value like xx and yy.
 //   stage C  VERTICAL pass first, on the packed pairs: a + 2b + c of three plane rows is two 32-bit integer operations for
 //            two pixels (every half stays below 2^16: 4 * 16129, 4 * 15417); the horizontal [1 2 1] is then two IDP.2A per
-//            pixel and plane on the 16-bit column sums -- 19 instructions per output row and plane instead of 28.5, and
+//            pixel and plane on the 16-bit column sums (two coefficient words, no byte permutes) -- 16 instructions per
+//            output row and plane instead of 28.5, and
 //            no accumulators that live across rows (version 2 spilled two of its 48).
 // ================================================================================================
 constexpr int H3_TIN_STRIDE = 160, H3_TIN_ROWS = 37;  // byte (r, t) <-> input (gy0 - 2 + r, gx0 - 16 + t); the TMA box is 160 x 36
@@ -365,40 +366,10 @@ constexpr int H3_NT = 256;
 constexpr int H3_XY_BIAS = 8192;
 constexpr unsigned H3_BOX_BYTES = 160 * 36;
 
-template <int MINB>
-__global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid_constant__ HarrisParams p, const __grid_constant__ CUtensorMap tmap) {
-    __shared__ __align__(128) unsigned char tin[H3_TIN_ROWS * H3_TIN_STRIDE];
-    __shared__ __align__(16) unsigned short sxx[H3_PL_ROWS * H3_PL_COLS];
-    __shared__ __align__(16) unsigned short syy[H3_PL_ROWS * H3_PL_COLS];
-    __shared__ __align__(16) unsigned short sxy[H3_PL_ROWS * H3_PL_COLS];
-    __shared__ __align__(8) uint64_t bar;
-
-    const int tid = threadIdx.x;
-    const int gx0 = blockIdx.x * HTW, gy0 = blockIdx.y * HTH;
-
-    // ---- stage A
-    {
-        const int x_need = p.in_ox + gx0 - 4, y_start = p.in_oy + gy0 - 2;   // image coordinates of (r = 0, t = 12)
-        const bool interior = x_need >= p.win.lo_x && x_need + 136 <= p.win.hi_x && y_start >= p.win.lo_y && y_start + 36 <= p.win.hi_y;
-        if (interior) {
-            if (tid == 0) {
-                mbar_init(&bar, 1);
-                mbar_fence_init();
-                mbar_arrive_expect_tx(&bar, H3_BOX_BYTES);
-                tma_load_2d(tin, &tmap, x_need - 12, y_start, &bar);   // 16-byte aligned origin (launch condition: in_ox % 16 == 0)
-            }
-            __syncthreads();   // the initialised barrier is visible to the waiting threads
-            mbar_wait(&bar, 0);
-        } else {
-            ImgRef<uchar> im{p.in, p.in_stride, p.in_iw, p.in_ih};
-            for (int e = tid; e < 36 * 136; e += H3_NT) {
-                const int r = e / 136, c = e - r * 136;
-                tin[r * H3_TIN_STRIDE + 12 + c] = fetch_bh(im, p.win, x_need + c, y_start + r, (uchar)0);
-            }
-            __syncthreads();
-        }
-    }
-
+// the three stages of version 3 on one 128 x 32 tile whose input bytes are staged in `tin`; every thread of the CTA calls
+// it (it synchronises); gx0 / gy0 = tile origin
+__device__ __forceinline__ void h3_tile(const HarrisParams &p, const unsigned char *tin, unsigned short *sxx, unsigned short *syy, unsigned short *sxy,
+                                        const int tid, const int gx0, const int gy0) {
     // ---- stage B: group g = intermediate columns jx = 4g - 2 .. 4g + 1 (plane columns 4g + 4 ..), chunk k = plane rows 5k .. 5k + 4
     if (tid < 33 * 7) {
         const int g = tid % 33, k = tid / 33;
@@ -465,6 +436,7 @@ __global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid
     uchar *dst = p.out + (size_t)(p.out_oy + gyb) * p.out_stride + p.out_ox + gx;
     const bool vec = gx + 3 < p.w && ((reinterpret_cast<uintptr_t>(dst) | (unsigned)p.out_stride) & 3u) == 0;
     constexpr unsigned cw = 0x00010201u;   // dp2a.lo: (1, 2) on (v[i-1], v[i]); dp2a.hi: (1, 0) on (v[i+1], v[i+2])
+    constexpr unsigned ce = 0x01020100u;   // dp2a.lo: (0, 1) on (v[i-2], v[i-1]); dp2a.hi: (2, 1) on (v[i], v[i+1])
     const int o0 = 4 * ty * H3_PL_COLS + 4 * tx + 4;   // plane columns 4tx + 4 .. 4tx + 11 (8-byte aligned)
     const unsigned short *pl0 = sxx + o0, *pl1 = syy + o0, *pl2 = sxy + o0;
     uint2 ra[3][2], rb[3][2];
@@ -487,11 +459,13 @@ __global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid
                 const unsigned V0 = mad_u32(rb[pl][0].x, 2u, ra[pl][0].x) + c0.x, V1 = mad_u32(rb[pl][0].y, 2u, ra[pl][0].y) + c0.y;
                 const unsigned V2 = mad_u32(rb[pl][1].x, 2u, ra[pl][1].x) + c1.x, V3 = mad_u32(rb[pl][1].y, 2u, ra[pl][1].y) + c1.y;
                 ra[pl][0] = rb[pl][0]; ra[pl][1] = rb[pl][1]; rb[pl][0] = c0; rb[pl][1] = c1;
-                const unsigned p12 = __byte_perm(V0, V1, 0x5432), p34 = __byte_perm(V1, V2, 0x5432), p56 = __byte_perm(V2, V3, 0x5432);
+                // Vk = (v[2k], v[2k+1]); pixel i needs v[i+1] + 2 v[i+2] + v[i+3].  Odd pixels start on a register boundary
+                // (weights (1, 2) | (1, 0)); even pixels straddle it, which the OTHER coefficient word absorbs
+                // (weights (0, 1) | (2, 1)) -- no byte permutes to realign the pairs
                 const int init = pl == 2 ? -16 * H3_XY_BIAS : 0;
-                G[pl][0] = dp2a_hi_uu(p34, cw, dp2a_lo_uu(p12, cw, init));
+                G[pl][0] = dp2a_hi_uu(V1, ce, dp2a_lo_uu(V0, ce, init));
                 G[pl][1] = dp2a_hi_uu(V2, cw, dp2a_lo_uu(V1, cw, init));
-                G[pl][2] = dp2a_hi_uu(p56, cw, dp2a_lo_uu(p34, cw, init));
+                G[pl][2] = dp2a_hi_uu(V2, ce, dp2a_lo_uu(V1, ce, init));
                 G[pl][3] = dp2a_hi_uu(V3, cw, dp2a_lo_uu(V2, cw, init));
             }
             unsigned o = 0;
@@ -514,6 +488,43 @@ __global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid
             dst += p.out_stride;
         }
     }
+}
+
+// One tile per CTA: the co-resident CTAs (5 per SM) cover each other's TMA latency and barriers.  Two vertically adjacent
+// tiles per CTA with both TMA requests issued up front were measured slower (476-490 vs 512 Gpx/s: more registers or spills,
+// and a CTA's two tiles serialise on its plane buffers).
+template <int MINB>
+__global__ void __launch_bounds__(H3_NT, MINB) harris_fused3_kernel(const __grid_constant__ HarrisParams p, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) unsigned char tin[H3_TIN_ROWS * H3_TIN_STRIDE];
+    __shared__ __align__(16) unsigned short sxx[H3_PL_ROWS * H3_PL_COLS];
+    __shared__ __align__(16) unsigned short syy[H3_PL_ROWS * H3_PL_COLS];
+    __shared__ __align__(16) unsigned short sxy[H3_PL_ROWS * H3_PL_COLS];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int gx0 = blockIdx.x * HTW, gy0 = blockIdx.y * HTH;
+
+    // ---- stage A
+    const int x_need = p.in_ox + gx0 - 4, y_start = p.in_oy + gy0 - 2;   // image coordinates of (r = 0, t = 12)
+    const bool interior = x_need >= p.win.lo_x && x_need + 136 <= p.win.hi_x && y_start >= p.win.lo_y && y_start + 36 <= p.win.hi_y;
+    if (interior) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(&bar, H3_BOX_BYTES);
+            tma_load_2d(tin, &tmap, x_need - 12, y_start, &bar);   // 16-byte aligned origin (launch condition: in_ox % 16 == 0)
+        }
+        __syncthreads();   // the initialised barrier is visible to the waiting threads
+        mbar_wait(&bar, 0);
+    } else {   // border tiles: all threads, through CLAMP
+        ImgRef<uchar> im{p.in, p.in_stride, p.in_iw, p.in_ih};
+        for (int e = tid; e < 36 * 136; e += H3_NT) {
+            const int r = e / 136, c = e - r * 136;
+            tin[r * H3_TIN_STRIDE + 12 + c] = fetch_bh(im, p.win, x_need + c, y_start + r, (uchar)0);
+        }
+        __syncthreads();
+    }
+    h3_tile(p, tin, sxx, syy, sxy, tid, gx0, gy0);
 }
 
 }  // namespace hb
