@@ -800,6 +800,29 @@ def test_binning_kinds_roi_and_dropped_indices(hb, oracle, dev):
     assert got[17] == const.size and got.sum() == const.size
 
 
+def test_binning_pixels_of_no_bin_take_the_spare_word(hb, dev):
+    """The branch-free shared-memory path steers pixels of no bin to a spare word instead of branching around the atomic:
+    NaN, +-inf, values <= -1 (after scaling), >= num_bins and huge magnitudes are dropped, (-1, 0) counts in bin 0 like
+    the C conversion `(uint)v` -- the contract stated in hipacc_b200.h; the rest of the image is counted exactly."""
+    rng = np.random.default_rng(5)
+    base = (rng.random((97, 260)) * 254.0).astype(np.float32)
+    want = np.bincount((base / np.float32(255.0) * np.float32(256.0)).astype(np.int64).ravel(), minlength=256).astype(np.uint32)
+    img = np.concatenate([base, np.zeros((1, 260), np.float32)], axis=0)
+    special = [np.nan, np.inf, -np.inf, -1.0, -300.0, 255.0, 1e9, 3e38, -3e38, 1e30, -0.25, -0.9, 254.9999]
+    img[-1, :] = 10.0
+    img[-1, :len(special)] = special
+    want[int(np.float32(10.0) / np.float32(255.0) * np.float32(256.0))] += 260 - len(special)
+    want[0] += 2            # -0.25 and -0.9 scale into (-1, 0): (uint) truncation gives bin 0
+    want[255] += 1          # 254.9999
+    for padded in (True, False):
+        np.testing.assert_array_equal(hb.binning(to_dev(hb, img, dev, padded), 256), want)
+    # unscaled index kind on float pixels
+    f = np.array([[0.0, 0.99, 1.0, 63.5, 64.0, -0.5, -1.0, np.nan, np.inf, 1e20] * 8], np.float32)
+    w2 = np.zeros(64, np.uint32)
+    w2[0] = 3 * 8; w2[1] = 8; w2[63] = 8
+    np.testing.assert_array_equal(hb.binning(to_dev(hb, f, dev), 64, A.BIN_INDEX_PIXEL), w2)
+
+
 def test_histogram_full_size_properties(hb, dev):
     """8192^2 float (C3's image): counts sum to the pixel count and match torch.histc-free integer binning on the device"""
     import torch
