@@ -491,6 +491,15 @@ def test_harris_noise_image(hb, oracle, dev):
     np.testing.assert_array_equal(to_np(hb.harris(to_dev(hb, img, dev))), oracle.harris(img))
 
 
+def test_harris_extreme_gradients(hb, oracle, dev):
+    """Binary noise, diagonal steps, checkerboards and stripes: the Sobel sums and the biased dx*dy plane of the fused kernel
+    at their extremes (tests/test_oracle.py::test_harris_product_bound_behind_the_biased_xy_plane states the bound)."""
+    from test_oracle import _harris_extreme_images
+    for k, img in enumerate(_harris_extreme_images()):
+        big = np.tile(img, (3, 3))     # several tiles: interior (TMA-staged) and border tiles
+        np.testing.assert_array_equal(to_np(hb.harris(to_dev(hb, big, dev))), oracle.harris(big), err_msg=f"image {k}")
+
+
 @pytest.mark.parametrize("R", [2, 3])
 def test_harris_strips_with_ghost_rows_equal_the_whole(hb, oracle, dev, R):
     """C4 sharding: each strip + R >= 2 ghost rows of real neighbour data gives exactly its rows of the full result

@@ -418,6 +418,35 @@ def test_fast_cpu_harris_equals_generic_oracle(oracle, shape):
     np.testing.assert_array_equal(oracle.harris_fast(pitched[:, :w]), oracle.harris(np.ascontiguousarray(pitched[:, :w])))
 
 
+def _harris_extreme_images():
+    """images that drive the Sobel sums of the Harris pipeline to their extremes: binary noise, a diagonal step (both
+    derivatives at 510 = the largest |dx*6| the corner sharing allows next to an equal |dy*6|), checkerboards, stripes"""
+    rng = np.random.default_rng(99)
+    h, w = 96, 160
+    yy, xx = np.indices((h, w))
+    imgs = [(rng.integers(0, 2, size=(h, w)) * 255).astype(np.uint8) for _ in range(4)]
+    imgs += [((xx + yy) > 120).astype(np.uint8) * 255, ((xx - yy) > 20).astype(np.uint8) * 255,
+             ((xx + yy) % 2 * 255).astype(np.uint8), ((xx // 2 + yy // 2) % 2 * 255).astype(np.uint8),
+             ((xx % 3 == 0) * 255).astype(np.uint8), ((yy % 3 == 0) * 255).astype(np.uint8),
+             (rng.integers(0, 2, size=(h, w)) * 255 * ((xx + yy) > 100)).astype(np.uint8)]
+    return imgs
+
+
+def test_harris_product_bound_behind_the_biased_xy_plane(oracle):
+    """The fused kernel stores dx*dy with a bias of 8192 in an unsigned 16-bit plane and sums three rows of it in packed
+    16-bit halves: that needs |dx * dy| <= 7225 (the two Sobel sums share their corner pixels: |dx*6| + |dy*6| <= 1020).
+    Checked here on the oracle's intermediates for images built to hit the extremes; the diagonal step reaches the bound."""
+    worst = 0
+    for img in _harris_extreme_images():
+        dx = oracle.local_op(S.harris_deriv(M.HARRIS_DX), img).astype(np.int64)
+        dy = oracle.local_op(S.harris_deriv(M.HARRIS_DY), img).astype(np.int64)
+        assert np.abs(dx).max() <= 127 and np.abs(dy).max() <= 127
+        assert (np.abs(dx) * 6 + np.abs(dy) * 6).max() <= 1020 + 10          # quotients are truncated: |q| * 6 <= |d * 6|
+        worst = max(worst, int(np.abs(dx * dy).max()))
+    assert worst <= 7225
+    assert worst == 7225      # the diagonal step attains it: the bound is tight, not merely safe
+
+
 def test_fast_cpu_leg_refuses_what_it_does_not_specialise(oracle):
     u = synth.image_np("uint8", 40, 30, seed=73)
     with pytest.raises(RuntimeError):
