@@ -590,10 +590,18 @@ def named_operators(hb, dev, world, rank, stream, p2p, peak, parity, args):
         if halo is not None:
             halo.check()
         del buf, out
+    # the two side legs of C4 must never cost the line its headline (2 GiB of pinned host memory, a host with few cores ...)
     if world == 1 and not args.no_e2e:
-        entry["e2e"] = c4_e2e(hb, dev, stream, whole, whole_out, Wc, Hc)
+        try:
+            entry["e2e"] = c4_e2e(hb, dev, stream, whole, whole_out, Wc, Hc)
+        except Exception as e:  # noqa: BLE001
+            entry["e2e"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
     if world == 1 and rank == 0 and not args.no_cpu:
-        entry["cpu"] = c4_cpu()
+        try:
+            entry["cpu"] = c4_cpu()
+        except Exception as e:  # noqa: BLE001
+            entry["cpu"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     res["C4_harris_32768x32768"] = entry
     del whole, whole_out
 
