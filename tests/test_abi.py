@@ -118,3 +118,57 @@ def test_pair_kernel_sass_keeps_multiply_and_add_separately_rounded():
     sass = subprocess.run([cuobjdump, "-sass", obj], capture_output=True, text=True, check=True).stdout
     assert "FMUL2" in sass and "FADD2" in sass
     assert "FFMA2" not in sass   # (scalar FFMA does appear: the correctly rounded division of the DIVF epilogue)
+
+
+def _sass_of(obj_name, kernel_substr):
+    """SASS text of the kernels of one object whose mangled name contains `kernel_substr` (cuobjdump; no GPU needed)"""
+    import shutil
+    import subprocess
+    from hipacc_b200 import build as hb_build
+    hb_build.build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", os.path.join(os.path.dirname(hb_build.LIB), obj_name)], capture_output=True, text=True, check=True).stdout
+    keep, on = [], False
+    for line in out.splitlines():
+        if "Function :" in line:
+            on = kernel_substr in line
+        if on:
+            keep.append(line)
+    assert keep, f"no kernel matching {kernel_substr} in {obj_name}"
+    return "\n".join(keep)
+
+
+def test_harris_v3_sass_is_tma_staged_and_dot_product_based():
+    """hb_harris.cu version 3: the byte tile arrives by TMA on an mbarrier, the Sobel sums and the binomial run on the integer
+    dot-product instructions, the default instantiation (5 CTAs per SM) has no local-memory spills, and stage C realigns
+    nothing with byte permutes (the 21 PRMT left are the byte windows of stage B, three per staged input row)."""
+    sass = _sass_of("hb_harris.o", "harris_fused3_kernelILi5E")
+    assert "UTMALDG.2D" in sass and "SYNCS.ARRIVE.TRANS64" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass
+    assert sass.count("IDP.4A") >= 56 and sass.count("IDP.2A") >= 96
+    assert "STL" not in sass and "LDL" not in sass
+    assert sass.count("PRMT") <= 30
+
+
+def test_pyr_down_and_local_tma_sass_use_tma():
+    for obj, kern in (("hb_pyramid.o", "pyr_down_fused_kernelILi5ELb1ELi6E"), ("hb_local_tma.o", "local_tma_f32_kernel")):
+        sass = _sass_of(obj, kern)
+        assert "UTMALDG.2D" in sass and "SYNCS.PHASECHK.TRANS64.TRYWAIT" in sass, (obj, kern)
+    # the TMA-staged instantiation of the fused down step is the 6-CTA one: 40 registers, and what spills sits in the
+    # border tiles' loader only (the 5-CTA instantiation, used when TMA cannot address the image, has none)
+    assert "STL" not in _sass_of("hb_pyramid.o", "pyr_down_fused_kernelILi5ELb1ELi5E")
+
+
+def test_binning_sass_is_branch_free_shared_atomics():
+    """hb_binning.cu, shared-memory path: native shared-memory atomics (ATOMS), no generic-address ATOM, and the four pixels
+    of a 16-byte load are binned without a branch between their atomics."""
+    sass = _sass_of("hb_binning.o", "binning_kernelIfLi0ELi0ELb1ELb1E")
+    assert "ATOMS" in sass
+    lines = [l for l in sass.splitlines() if "/*0" in l or "/*1" in l or "/*2" in l or "/*3" in l]
+    idx = [i for i, l in enumerate(lines) if "ATOMS" in l]
+    runs = [b - a for a, b in zip(idx, idx[1:])]
+    assert runs and min(runs) <= 2          # consecutive atomics of one vector sit next to each other ...
+    first = idx[0]
+    assert not any("BRA" in l for l in lines[first:first + 6])   # ... with no branch in between
+    assert "ATOM.E" not in sass.replace("ATOMS", "")
