@@ -447,6 +447,20 @@ def test_harris_product_bound_behind_the_biased_xy_plane(oracle):
     assert worst == 7225      # the diagonal step attains it: the bound is tight, not merely safe
 
 
+def test_harris_oracle_and_fast_leg_equal_the_reference_dsl_on_extreme_images(ref):
+    """The compiled reference DSL (the sample's own nine kernel classes, oracle/_ref) on the extreme-gradient images and on
+    noise: the restated pipeline and the specialised CPU leg give the same corners and the same three smoothed planes."""
+    imgs = _harris_extreme_images() + [synth.image_np("uint8", 131, 77, seed=s) for s in (31, 32)]
+    for k, img in enumerate(imgs):
+        want, gx, gy, gxy = ref.ref_harris_u8(img)
+        got, ogx, ogy, ogxy = ref.harris(img, return_intermediates=True)
+        np.testing.assert_array_equal(ogx, gx, err_msg=f"image {k}")
+        np.testing.assert_array_equal(ogy, gy, err_msg=f"image {k}")
+        np.testing.assert_array_equal(ogxy, gxy, err_msg=f"image {k}")
+        np.testing.assert_array_equal(got, want, err_msg=f"image {k}")
+        np.testing.assert_array_equal(ref.harris_fast(img), want, err_msg=f"image {k} (fast leg)")
+
+
 def test_fast_cpu_leg_refuses_what_it_does_not_specialise(oracle):
     u = synth.image_np("uint8", 40, 30, seed=73)
     with pytest.raises(RuntimeError):
