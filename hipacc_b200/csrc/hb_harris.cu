@@ -357,8 +357,9 @@ __global__ void __launch_bounds__(H2_NT, 6) harris_fused2_kernel(const __grid_co
 //   stage C  VERTICAL pass first, on the packed pairs: a + 2b + c of three plane rows is two 32-bit integer operations for
 //            two pixels (every half stays below 2^16: 4 * 16129, 4 * 15417); the horizontal [1 2 1] is then two IDP.2A per
 //            pixel and plane on the 16-bit column sums (two coefficient words, no byte permutes) -- 16 instructions per
-//            output row and plane instead of 28.5, and
-//            no accumulators that live across rows (version 2 spilled two of its 48).
+//            output row and plane instead of 28.5, and no accumulators that live across rows (version 2 spilled two of
+//            its 48).
+// 60 instructions per pixel instead of 86; 363 -> 528 Gpx/s on the 32768^2 image.
 // ================================================================================================
 constexpr int H3_TIN_STRIDE = 160, H3_TIN_ROWS = 37;  // byte (r, t) <-> input (gy0 - 2 + r, gx0 - 16 + t); the TMA box is 160 x 36
 constexpr int H3_PL_COLS = 136, H3_PL_ROWS = 35;      // plane (q, c) <-> intermediate position (jy, jx) = (q - 1, c - 6)
