@@ -57,6 +57,20 @@ SAMPLES = {
     "6_Test/Kernel_Fusion_P2P": "PASSED",
 }
 
+# Samples that are only BUILT (unmodified, like the ones above): they compile against the front for the device, which is
+# what says the DSL surface they use exists; they are not part of the GPU run list -- Optical_Flow and Motion_Interpolation
+# abort on a DSL assert in the reference itself (an accessor that is never registered), the other
+# five carry no comparison against a C reference and were added after the round's GPU time was spent.
+BUILD_ONLY = {
+    "3_Preprocessing/Optical_Flow": "BUILDS",
+    "4_Postprocessing/Bokeh_Effect": "BUILDS",
+    "4_Postprocessing/Chromatic_Abberation": "BUILDS",
+    "5_Other/Game_of_Life": "BUILDS",
+    "5_Other/Mandelbrot": "BUILDS",
+    "5_Other/Motion_Interpolation": "BUILDS",
+    "5_Other/WCE_Enhance": "BUILDS",
+}
+
 
 def name_of(sample):
     return os.path.basename(sample)
@@ -88,7 +102,8 @@ def build_all(jobs=8):
     hb_build.build()
     failed = {}
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
-        for sample, (exe, log) in zip(SAMPLES, ex.map(build_one, SAMPLES)):
+        todo = list(SAMPLES) + list(BUILD_ONLY)
+        for sample, (exe, log) in zip(todo, ex.map(build_one, todo)):
             if exe is None:
                 failed[sample] = log
     return failed
@@ -100,4 +115,5 @@ if __name__ == "__main__":
     bad = build_all()
     for s, log in bad.items():
         print("FAILED to build", s, "\n", log[-2000:])
-    print(f"built {len(SAMPLES) - len(bad)} of {len(SAMPLES)} reference samples into {OUT}")
+    n = len(SAMPLES) + len(BUILD_ONLY)
+    print(f"built {n - len(bad)} of {n} reference samples into {OUT}")
