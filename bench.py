@@ -163,10 +163,11 @@ def run_reference(args):
     }))
 
 
-def measured_traffic(kernel_substr):
+def measured_traffic(kernel_substr, grid_x=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel whose name contains `kernel_substr`, from the
     newest committed ncu launch list (profiles/*launches*.csv, `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
-    dram__bytes_write.sum`); None when no list carries the metric.  -> (bytes per launch, source file)"""
+    dram__bytes_write.sum`); None when no list carries the metric.  grid_x: only launches with that many CTAs (the list
+    also holds the same kernel on smaller images).  -> (bytes per launch, source file)"""
     import csv
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*launches*.csv")), key=lambda f: (os.path.basename(f).split("_")[0], os.path.getmtime(f)))
@@ -177,7 +178,11 @@ def measured_traffic(kernel_substr):
                 rows = [r for r in csv.reader(l for l in fh if l.startswith('"'))]
             hdr = rows[0]
             iK, iM, iV, iI = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+            iG = hdr.index("Grid Size") if "Grid Size" in hdr else None
+            want_grid = None if grid_x is None or iG is None else f"({int(grid_x)}, 1, 1)"
             for r in rows[1:]:
+                if want_grid is not None and r[iG] != want_grid:
+                    continue
                 if kernel_substr in r[iK] and r[iM] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     per_id[r[iI]] = per_id.get(r[iI], 0.0) + float(r[iV].replace(",", ""))
             if per_id:
@@ -346,7 +351,7 @@ def main():
                 "traffic": None, "kernel": "local_tma_f32_kernel<3,3,Mask*> (TMA-staged, one 128x32 tile per CTA)",
                 "note": "frac can slightly exceed 1: consecutive operators re-read the same 256 MiB input and a part of it still sits in the 126 MB L2; single-operator launches reach 0.95 (operators.C2_*)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_PX * W * plan.rows, "avg_launch_ms": per_launch_ms}
-    roofline["traffic"], roofline["traffic_source"] = measured_traffic("local_tma_f32_kernel<3, 3")
+    roofline["traffic"], roofline["traffic_source"] = measured_traffic("local_tma_f32_kernel<3, 3", grid_x=((W + 127) // 128) * ((plan.rows + 31) // 32))
 
     # ---- e2e: the same step through the C-ABI memory calls with HOST (pinned) buffers, copies inside the timed region
     L = hb.lib()
