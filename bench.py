@@ -349,7 +349,7 @@ def main():
     achieved = ALG_BYTES_PER_PX * W * plan.rows / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "local_tma_f32_kernel<3,3,Mask*> (TMA-staged, one 128x32 tile per CTA)",
-                "note": "frac can slightly exceed 1: consecutive operators re-read the same 256 MiB input and a part of it still sits in the 126 MB L2; single-operator launches reach 0.95 (operators.C2_*)", "peak_source": peak_src,
+                "note": "frac can slightly exceed 1: consecutive operators re-read the same 256 MiB input and a part of it still sits in the 126 MB L2; isolated single-operator launches (--extra: operators.C2_*) measure 0.98-1.02", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_PX * W * plan.rows, "avg_launch_ms": per_launch_ms}
     roofline["traffic"], roofline["traffic_source"] = measured_traffic("local_tma_f32_kernel<3, 3", grid_x=((W + 127) // 128) * ((plan.rows + 31) // 32))
 
